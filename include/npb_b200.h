@@ -1,0 +1,138 @@
+/*
+ * npb_b200.h -- C ABI of libnpb_b200.so, the B200 (sm_100a) backend for the
+ * NPBench structured-grid stencil family.
+ *
+ * This is the drop-in boundary: plain C, raw pointers and sizes, no C++/torch
+ * types.  The NPBench side binds it with ctypes (npbench_b200/_lib.py; the
+ * stub a reference maintainer would add is in INTEGRATION.md).  Citations are
+ * file:line inside spcl/npbench.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     npb_last_error() then returns a static, human readable message;
+ *   - one process drives one GPU (npb_init(device)); library state is process
+ *     global, calls are not re-entrant (the NPBench harness is single threaded:
+ *     npbench/infrastructure/test.py:16-51);
+ *   - kernel entry points taking DEVICE pointers only enqueue work on the
+ *     library's current stream and return; npb_sync() is the blocking call
+ *     (same semantics the CuPy plugin gets from stream.synchronize(),
+ *     npbench/infrastructure/cupy_framework.py:47-58);
+ *   - *_host entry points take HOST pointers: they copy in, run, copy the
+ *     validated outputs back and return after synchronising -- the exact call
+ *     a NumPy user makes (in-place mutation, bench_info/<b>.json output_args);
+ *   - all arrays are C-contiguous float64 (checked by the Python side:
+ *     every NPBench array_arg is);
+ *   - results are bit-identical to NPBench's NumPy implementations: kernels
+ *     keep NumPy's evaluation order and are compiled with -fmad=false.
+ */
+#ifndef NPB_B200_H
+#define NPB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ---------------------------------------------------------- */
+int npb_init(int device);                /* select device, create stream + pool; idempotent */
+int npb_shutdown(void);
+const char *npb_version(void);           /* Framework.version(): framework.py:33-35 */
+const char *npb_last_error(void);
+int npb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes,
+                    size_t *smem_per_block_optin, size_t *total_mem);
+
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) for all
+ * subsequent calls; NULL restores the library stream. */
+int npb_set_stream(void *cuda_stream);
+void *npb_get_stream(void);
+int npb_sync(void);                      /* the sync appended to exec_str (cupy_framework.py:56-58) */
+
+/* ---- device memory: what Framework.copy_func / copy_back_func need
+ *      (framework.py:42-50; called once per array per repetition,
+ *      framework.py:147-150) -- a caching pool, no cudaFree on the hot path */
+int npb_malloc(size_t bytes, void **dptr);
+int npb_free(void *dptr);
+int npb_pool_trim(void);                 /* return cached blocks to the driver */
+int npb_host_alloc(size_t bytes, void **hptr);   /* pinned host memory */
+int npb_host_free(void *hptr);
+int npb_h2d(void *dst_dev, const void *src_host, size_t bytes);   /* async on the stream */
+int npb_d2h(void *dst_host, const void *src_dev, size_t bytes);   /* async on the stream */
+int npb_d2d(void *dst_dev, const void *src_dev, size_t bytes);
+int npb_memset(void *dst_dev, int value, size_t bytes);
+
+/* ---- timing / accounting ---------------------------------------------- */
+int npb_timer_start(void);               /* cudaEventRecord on the current stream */
+int npb_timer_stop(float *ms);           /* record + synchronise + elapsed */
+uint64_t npb_launch_count(void);         /* kernels launched by this library so far */
+int npb_l2_flush(void);                  /* overwrite a buffer larger than L2 */
+
+/* ---- the five kernels, DEVICE pointers -------------------------------- */
+
+/* kernel(TSTEPS, A, B): polybench/jacobi_2d/jacobi_2d_numpy.py:4-10.
+ * A, B (ni, nj); 2*(TSTEPS-1) sweeps; both A and B are outputs. */
+int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B);
+
+/* One temporally blocked pass: `nsteps` (odd, 1..NPB_JACOBI2D_MAX_BLOCK)
+ * sweeps src -> dst fused in shared memory, restricted to tile rows
+ * [tile_row_lo, tile_row_hi) (pass 0, -1 for all).  Building block of the
+ * slab-sharded multi-GPU driver (boundary tiles first, interior overlapped
+ * with the halo exchange). */
+#define NPB_JACOBI2D_MAX_BLOCK 7
+int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst,
+                           int64_t tile_row_lo, int64_t tile_row_hi);
+int npb_jacobi2d_tile_rows(void);        /* rows per tile of the blocked kernel */
+
+/* kernel(TSTEPS, A, B): polybench/heat_3d/heat_3d_numpy.py:4-20.  (n0,n1,n2). */
+int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B);
+/* one sweep src -> dst over planes [i_lo, i_hi) (clamped to the interior) */
+int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
+                         int64_t i_lo, int64_t i_hi);
+
+/* kernel(TMAX, ex, ey, hz, _fict_): polybench/fdtd_2d/fdtd_2d_numpy.py:4-11. */
+int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz,
+                   const double *fict);
+/* one fused time step on a row slab: local rows [0, nrows) are global rows
+ * [row0, row0+nrows) of an nx_global-row grid; src fields -> dst fields
+ * (out of place); `fict_t` is _fict_[t].  Rows whose stencil leaves the slab
+ * are copied (they are ghost rows of the sharded driver). */
+int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
+                        const double *ex, const double *ey, const double *hz,
+                        double *ex_out, double *ey_out, double *hz_out, double fict_t);
+
+/* hdiff(in_field, out_field, coeff): weather_stencils/hdiff/hdiff_numpy.py:5-29.
+ * in (I+4, J+4, K); out, coeff (I, J, K). */
+int npb_hdiff_f64(int64_t I, int64_t J, int64_t K, const double *in_field, double *out_field,
+                  const double *coeff);
+
+/* vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage):
+ * weather_stencils/vadv/vadv_numpy.py:9-78.  All (I,J,K) but wcon (I+1,J,K). K >= 2. */
+int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
+                 const double *wcon, const double *u_pos, const double *utens, double dtr_stage);
+
+/* ---- the same five calls on HOST buffers (copy in, run, copy outputs back,
+ *      synchronise): the NumPy-signature call of bench_info/<b>.json ------- */
+int npb_jacobi2d_f64_host(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B);
+int npb_heat3d_f64_host(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B);
+int npb_fdtd2d_f64_host(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz,
+                        const double *fict);
+int npb_hdiff_f64_host(int64_t I, int64_t J, int64_t K, const double *in_field, double *out_field,
+                       const double *coeff);
+int npb_vadv_f64_host(int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
+                      const double *wcon, const double *u_pos, const double *utens,
+                      double dtr_stage);
+
+/* ---- device-side initialisers (NPBench `initialize`, closed forms):
+ *      jacobi_2d.py:6-10, heat_3d.py:6-11, fdtd_2d.py:6-15.  Rows
+ *      [row0, row0+nrows) of the global grid, for the scaled / sharded grids. */
+int npb_init_jacobi2d_f64(int64_t n_global, int64_t row0, int64_t nrows, int64_t ncols, double *A,
+                          double *B);
+int npb_init_heat3d_f64(int64_t n_global, int64_t row0, int64_t nrows, double *A, double *B);
+int npb_init_fdtd2d_f64(int64_t tmax, int64_t nx_global, int64_t ny, int64_t row0, int64_t nrows,
+                        double *ex, double *ey, double *hz, double *fict);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPB_B200_H */

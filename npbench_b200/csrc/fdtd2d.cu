@@ -1,0 +1,113 @@
+// fdtd2d.cu -- 2-D FDTD (ex, ey, hz), one fused kernel per time step (sm_100a).
+//
+// Replaces kernel(TMAX, ex, ey, hz, _fict_),
+// npbench/benchmarks/polybench/fdtd_2d/fdtd_2d_numpy.py:4-11: four dependent
+// whole-array statements per step (11 ufunc passes).  Here one kernel per step
+// reads the old fields and writes the new ones out of place: the hz update
+// needs the NEW ex(i,j+1) and ey(i+1,j), which are recomputed in registers
+// from old values, so every field is read and written once per step (48 B per
+// cell) and no intermediate array is materialised.  Fields ping-pong between
+// the caller's arrays and a library workspace.
+//
+// Row-slab form: local rows [0,nrows) are global rows [row0,row0+nrows) of an
+// nx_global-row grid, so the same kernel serves the halo-sharded multi-GPU
+// driver (rows whose stencil leaves the slab are ghost rows: copied).
+//
+// Arithmetic in NumPy order, -fmad=false (oracle: npb_oracle_fdtd2d).
+#include "common.cuh"
+
+namespace {
+
+constexpr int FD_THREADS = 256;
+
+struct FdtdParams {
+    long long nx_global, row0, nrows, ny;
+    const double *ex, *ey, *hz;
+    double *exo, *eyo, *hzo;
+    const double *fict_ptr;   // if non-null, _fict_[t] is read from here
+    double fict_val;
+};
+
+__global__ void __launch_bounds__(FD_THREADS)
+fdtd2d_step_kernel(FdtdParams p) {
+    const long long j = (long long)blockIdx.y * FD_THREADS + threadIdx.x;
+    const long long i = blockIdx.x;   // local row
+    if (j >= p.ny) return;
+    const long long ny = p.ny;
+    const long long gi = p.row0 + i;
+    const long long o = i * ny + j;
+    const double hz_c = __ldg(p.hz + o);
+    const double ex_c = __ldg(p.ex + o);
+    const double ey_c = __ldg(p.ey + o);
+
+    // fdtd_2d_numpy.py:7-8
+    double ey_n;
+    if (gi == 0) {
+        ey_n = p.fict_ptr ? __ldg(p.fict_ptr) : p.fict_val;
+    } else if (i == 0) {
+        ey_n = ey_c;                                   // ghost row of a slab: no row above
+    } else {
+        ey_n = ey_c - 0.5 * (hz_c - __ldg(p.hz + o - ny));
+    }
+    // :9
+    double ex_n = ex_c;
+    if (j >= 1) ex_n = ex_c - 0.5 * (hz_c - __ldg(p.hz + o - 1));
+    // :10-11 (needs new ex(i,j+1) and new ey(i+1,j); both always take the update formula)
+    double hz_n = hz_c;
+    if (gi < p.nx_global - 1 && i < p.nrows - 1 && j < ny - 1) {
+        const double ex_r = __ldg(p.ex + o + 1) - 0.5 * (__ldg(p.hz + o + 1) - hz_c);
+        const double ey_d = __ldg(p.ey + o + ny) - 0.5 * (__ldg(p.hz + o + ny) - hz_c);
+        hz_n = hz_c - 0.7 * (((ex_r - ex_n) + ey_d) - ey_n);
+    }
+    p.exo[o] = ex_n;
+    p.eyo[o] = ey_n;
+    p.hzo[o] = hz_n;
+}
+
+int launch_step(const FdtdParams &p) {
+    if (p.nrows <= 0 || p.ny <= 0) return 0;
+    const long long jb = (p.ny + FD_THREADS - 1) / FD_THREADS;
+    if (jb > 65535 || p.nrows >= (1LL << 31)) return npb::fail("fdtd2d", "grid too large");
+    dim3 grid((unsigned)p.nrows, (unsigned)jb);
+    fdtd2d_step_kernel<<<grid, FD_THREADS, 0, npb::st().stream>>>(p);
+    NPB_CHECK_LAUNCH("fdtd2d_step_kernel");
+    npb::count_launch();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
+                                   const double *ex, const double *ey, const double *hz,
+                                   double *ex_out, double *ey_out, double *hz_out, double fict_t) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nrows >= 0 && ny >= 0 && row0 >= 0 && row0 + nrows <= nx_global, "npb_fdtd2d_step_f64",
+            "slab outside the grid");
+    FdtdParams p{nx_global, row0, nrows, ny, ex, ey, hz, ex_out, ey_out, hz_out, nullptr, fict_t};
+    return launch_step(p);
+}
+
+extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
+                              double *hz, const double *fict) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nx >= 0 && ny >= 0, "npb_fdtd2d_f64", "negative extent");
+    if (tmax <= 0 || nx == 0 || ny == 0) return 0;
+    const size_t cells = (size_t)nx * (size_t)ny;
+    double *ws = (double *)npb::workspace(0, 3 * cells * sizeof(double));
+    NPB_ARG(ws != nullptr, "npb_fdtd2d_f64", "cannot allocate the ping-pong workspace");
+    double *u[3] = {ex, ey, hz};
+    double *w[3] = {ws, ws + cells, ws + 2 * cells};
+    for (int64_t t = 0; t < tmax; ++t) {
+        double **s = (t & 1) ? w : u;
+        double **d = (t & 1) ? u : w;
+        FdtdParams p{nx, 0, nx, ny, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
+        const int rc = launch_step(p);
+        if (rc) return rc;
+    }
+    if (tmax & 1) {   // result lives in the workspace: bring it home
+        for (int f = 0; f < 3; ++f)
+            NPB_CUDA(cudaMemcpyAsync(u[f], w[f], cells * sizeof(double), cudaMemcpyDeviceToDevice,
+                                     npb::st().stream));
+    }
+    return 0;
+}

@@ -1,0 +1,99 @@
+// host_api.cu -- the five kernels on HOST buffers: the call a NumPy user makes.
+//
+// Same signatures and in-place semantics as the NPBench NumPy functions
+// (bench_info/<b>.json: input_args / output_args): copy the array arguments to
+// the device (pool allocator), enqueue the kernel, copy the validated outputs
+// back, synchronise.  This is the path bench.py's `e2e` number times.
+#include "common.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) npb_free(p); }
+    int alloc(size_t bytes) { return npb_malloc(bytes, &p); }
+    double *d() const { return (double *)p; }
+};
+
+#define NPB_TRY(call)            \
+    do {                         \
+        int rc_ = (call);        \
+        if (rc_) return rc_;     \
+    } while (0)
+
+}  // namespace
+
+extern "C" int npb_jacobi2d_f64_host(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(ni >= 0 && nj >= 0, "npb_jacobi2d_f64_host", "negative extent");
+    const size_t bytes = (size_t)ni * (size_t)nj * sizeof(double);
+    if (!bytes) return 0;
+    DevBuf dA, dB;
+    NPB_TRY(dA.alloc(bytes)); NPB_TRY(dB.alloc(bytes));
+    NPB_TRY(npb_h2d(dA.p, A, bytes)); NPB_TRY(npb_h2d(dB.p, B, bytes));
+    NPB_TRY(npb_jacobi2d_f64(tsteps, ni, nj, dA.d(), dB.d()));
+    NPB_TRY(npb_d2h(A, dA.p, bytes)); NPB_TRY(npb_d2h(B, dB.p, bytes));
+    return npb_sync();
+}
+
+extern "C" int npb_heat3d_f64_host(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A,
+                                   double *B) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(n0 >= 0 && n1 >= 0 && n2 >= 0, "npb_heat3d_f64_host", "negative extent");
+    const size_t bytes = (size_t)n0 * (size_t)n1 * (size_t)n2 * sizeof(double);
+    if (!bytes) return 0;
+    DevBuf dA, dB;
+    NPB_TRY(dA.alloc(bytes)); NPB_TRY(dB.alloc(bytes));
+    NPB_TRY(npb_h2d(dA.p, A, bytes)); NPB_TRY(npb_h2d(dB.p, B, bytes));
+    NPB_TRY(npb_heat3d_f64(tsteps, n0, n1, n2, dA.d(), dB.d()));
+    NPB_TRY(npb_d2h(A, dA.p, bytes)); NPB_TRY(npb_d2h(B, dB.p, bytes));
+    return npb_sync();
+}
+
+extern "C" int npb_fdtd2d_f64_host(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
+                                   double *hz, const double *fict) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nx >= 0 && ny >= 0 && tmax >= 0, "npb_fdtd2d_f64_host", "negative extent");
+    const size_t bytes = (size_t)nx * (size_t)ny * sizeof(double);
+    if (!bytes || tmax == 0) return 0;
+    DevBuf dx, dy, dz, df;
+    NPB_TRY(dx.alloc(bytes)); NPB_TRY(dy.alloc(bytes)); NPB_TRY(dz.alloc(bytes));
+    NPB_TRY(df.alloc((size_t)tmax * sizeof(double)));
+    NPB_TRY(npb_h2d(dx.p, ex, bytes)); NPB_TRY(npb_h2d(dy.p, ey, bytes)); NPB_TRY(npb_h2d(dz.p, hz, bytes));
+    NPB_TRY(npb_h2d(df.p, fict, (size_t)tmax * sizeof(double)));
+    NPB_TRY(npb_fdtd2d_f64(tmax, nx, ny, dx.d(), dy.d(), dz.d(), df.d()));
+    NPB_TRY(npb_d2h(ex, dx.p, bytes)); NPB_TRY(npb_d2h(ey, dy.p, bytes)); NPB_TRY(npb_d2h(hz, dz.p, bytes));
+    return npb_sync();
+}
+
+extern "C" int npb_hdiff_f64_host(int64_t I, int64_t J, int64_t K, const double *in_field,
+                                  double *out_field, const double *coeff) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(I >= 0 && J >= 0 && K >= 0, "npb_hdiff_f64_host", "negative extent");
+    const size_t ob = (size_t)I * (size_t)J * (size_t)K * sizeof(double);
+    const size_t ib = (size_t)(I + 4) * (size_t)(J + 4) * (size_t)K * sizeof(double);
+    if (!ob) return 0;
+    DevBuf di, dout, dc;
+    NPB_TRY(di.alloc(ib)); NPB_TRY(dout.alloc(ob)); NPB_TRY(dc.alloc(ob));
+    NPB_TRY(npb_h2d(di.p, in_field, ib)); NPB_TRY(npb_h2d(dc.p, coeff, ob));
+    NPB_TRY(npb_hdiff_f64(I, J, K, di.d(), dout.d(), dc.d()));
+    NPB_TRY(npb_d2h(out_field, dout.p, ob));
+    return npb_sync();
+}
+
+extern "C" int npb_vadv_f64_host(int64_t I, int64_t J, int64_t K, double *utens_stage,
+                                 const double *u_stage, const double *wcon, const double *u_pos,
+                                 const double *utens, double dtr_stage) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(I >= 0 && J >= 0 && K >= 0, "npb_vadv_f64_host", "negative extent");
+    const size_t b = (size_t)I * (size_t)J * (size_t)K * sizeof(double);
+    const size_t bw = (size_t)(I + 1) * (size_t)J * (size_t)K * sizeof(double);
+    if (!b) return 0;
+    DevBuf d0, d1, d2, d3, d4;
+    NPB_TRY(d0.alloc(b)); NPB_TRY(d1.alloc(b)); NPB_TRY(d2.alloc(bw)); NPB_TRY(d3.alloc(b)); NPB_TRY(d4.alloc(b));
+    NPB_TRY(npb_h2d(d0.p, utens_stage, b)); NPB_TRY(npb_h2d(d1.p, u_stage, b));
+    NPB_TRY(npb_h2d(d2.p, wcon, bw)); NPB_TRY(npb_h2d(d3.p, u_pos, b)); NPB_TRY(npb_h2d(d4.p, utens, b));
+    NPB_TRY(npb_vadv_f64(I, J, K, d0.d(), d1.d(), d2.d(), d3.d(), d4.d(), dtr_stage));
+    NPB_TRY(npb_d2h(utens_stage, d0.p, b));
+    return npb_sync();
+}

@@ -1,0 +1,179 @@
+// jacobi2d.cu -- 5-point 2-D Jacobi, temporally blocked in shared memory (sm_100a).
+//
+// Replaces kernel(TSTEPS, A, B),
+// npbench/benchmarks/polybench/jacobi_2d/jacobi_2d_numpy.py:4-10
+// (2*(TSTEPS-1) sweeps ping-ponging A -> B -> A; borders of A and B are never
+// written, so every odd state carries B's border and every even state A's).
+//
+// One launch advances the grid by `nsteps` sweeps (odd, <= 7): a CTA loads an
+// output tile plus an nsteps-deep halo into shared memory, runs the sweeps on
+// a shrinking region between two shared buffers, and writes the tile centre.
+// Because nsteps is odd the pass always goes from one user array to the other
+// (no scratch copy of a possibly 50 GB grid), and HBM sees one read + one
+// write of the grid per nsteps sweeps.  Inside a sweep each thread owns a pair
+// of adjacent columns and marches down its row segment with a 3-row register
+// window (16-byte shared loads/stores for the pair, 8-byte for the two side
+// neighbours): 24 B of shared traffic per cell update.
+//
+// Arithmetic: 0.2*((((c + left) + right) + down) + up), NumPy's order
+// (oracle/stencil_oracle.c: jacobi2d_sweep); compiled with -fmad=false.
+#include "common.cuh"
+
+namespace {
+
+constexpr int JB_HP = 8;                       // halo padding (even, >= max nsteps)
+constexpr int JB_C = 128;                      // shared tile columns
+constexpr int JB_TJ = JB_C - 2 * JB_HP;        // 112 output columns per tile
+constexpr int JB_TI = 32;                      // output rows per tile
+constexpr int JB_R = JB_TI + 2 * NPB_JACOBI2D_MAX_BLOCK;   // 46 shared tile rows
+constexpr int JB_THREADS = 256;
+constexpr int JB_SEGS = JB_THREADS / (JB_C / 2);           // 4 row segments
+constexpr size_t JB_SMEM = (size_t)2 * JB_R * JB_C * sizeof(double);   // 94208 B
+
+__global__ void __launch_bounds__(JB_THREADS, 2)
+jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__restrict__ src,
+                      double *__restrict__ dst, long long tile_row0) {
+    extern __shared__ __align__(16) double sm[];
+    double *buf0 = sm;                 // states of src parity
+    double *buf1 = sm + JB_R * JB_C;   // states of dst parity
+    const int h = nsteps;
+    const long long i0 = 1 + (tile_row0 + blockIdx.y) * JB_TI;   // first output row
+    const long long j0 = 1 + (long long)blockIdx.x * JB_TJ;      // first output column
+    // shared (r, c)  <->  global (i0 - MAXB + r, j0 - HP + c)
+    const long long gi_base = i0 - NPB_JACOBI2D_MAX_BLOCK;
+    const long long gj_base = j0 - JB_HP;
+
+    // ---- load: rows [i0-h, i0+TI+h), cols [j0-h, j0+TJ+h), clipped to the grid
+    const long long r_lo = max(0LL, i0 - h), r_hi = min(ni - 1, i0 + JB_TI - 1 + h);
+    const long long c_lo = max(0LL, j0 - h), c_hi = min(nj - 1, j0 + JB_TJ - 1 + h);
+    for (int idx = threadIdx.x; idx < JB_R * JB_C; idx += JB_THREADS) {
+        const int r = idx / JB_C, c = idx % JB_C;
+        const long long gi = gi_base + r, gj = gj_base + c;
+        if (gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi) {
+            buf0[idx] = __ldg(src + gi * nj + gj);
+            if (gi == 0 || gi == ni - 1 || gj == 0 || gj == nj - 1)
+                buf1[idx] = __ldg((const double *)dst + gi * nj + gj);   // dst's own constant border
+        }
+    }
+    __syncthreads();
+
+    // ---- nsteps sweeps on a shrinking region
+    const int pair = threadIdx.x % (JB_C / 2);   // column pair: shared cols 2*pair, 2*pair+1
+    const int seg = threadIdx.x / (JB_C / 2);    // row segment
+    const int cs0 = 2 * pair;
+    for (int s = 1; s <= nsteps; ++s) {
+        const double *in = (s & 1) ? buf0 : buf1;
+        double *out = (s & 1) ? buf1 : buf0;
+        // update region in global coordinates, clipped to the interior
+        const long long ui_lo = max(1LL, i0 - h + s), ui_hi = min(ni - 2, i0 + JB_TI - 1 + h - s);
+        const long long uj_lo = max(1LL, j0 - h + s), uj_hi = min(nj - 2, j0 + JB_TJ - 1 + h - s);
+        const int rr_lo = (int)(ui_lo - gi_base), rr_hi = (int)(ui_hi - gi_base);   // shared rows
+        const int cc_lo = (int)(uj_lo - gj_base), cc_hi = (int)(uj_hi - gj_base);   // shared cols
+        const int nrows = rr_hi - rr_lo + 1;
+        if (nrows > 0 && cs0 + 1 >= cc_lo && cs0 <= cc_hi) {
+            const int per = (nrows + JB_SEGS - 1) / JB_SEGS;
+            const int ra = rr_lo + seg * per;
+            const int rb = min(rr_hi, ra + per - 1);
+            if (ra <= rb) {
+                const bool w0 = (cs0 >= cc_lo), w1 = (cs0 + 1 <= cc_hi);
+                const double *pin = in + ra * JB_C + cs0;
+                double *pout = out + ra * JB_C + cs0;
+                double2 up = *reinterpret_cast<const double2 *>(pin - JB_C);
+                double2 ce = *reinterpret_cast<const double2 *>(pin);
+                for (int r = ra; r <= rb; ++r) {
+                    const double2 dn = *reinterpret_cast<const double2 *>(pin + JB_C);
+                    const double left = pin[-1];
+                    const double right = pin[2];
+                    double2 res;
+                    res.x = 0.2 * ((((ce.x + left) + ce.y) + dn.x) + up.x);
+                    res.y = 0.2 * ((((ce.y + ce.x) + right) + dn.y) + up.y);
+                    if (w0 && w1) {
+                        *reinterpret_cast<double2 *>(pout) = res;
+                    } else if (w0) {
+                        pout[0] = res.x;
+                    } else {
+                        pout[1] = res.y;
+                    }
+                    up = ce; ce = dn;
+                    pin += JB_C; pout += JB_C;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store the tile centre (interior cells only) from the last buffer
+    const double *fin = (nsteps & 1) ? buf1 : buf0;
+    const long long o_ihi = min(ni - 2, i0 + JB_TI - 1), o_jhi = min(nj - 2, j0 + JB_TJ - 1);
+    for (int idx = threadIdx.x; idx < JB_TI * JB_TJ; idx += JB_THREADS) {
+        const int r = idx / JB_TJ, c = idx % JB_TJ;
+        const long long gi = i0 + r, gj = j0 + c;
+        if (gi <= o_ihi && gj <= o_jhi)
+            dst[gi * nj + gj] = fin[(r + NPB_JACOBI2D_MAX_BLOCK) * JB_C + (c + JB_HP)];
+    }
+}
+
+int launch_block(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst,
+                 int64_t tr_lo, int64_t tr_hi) {
+    static bool configured = false;
+    if (!configured) {
+        NPB_CUDA(cudaFuncSetAttribute(jacobi2d_block_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_SMEM));
+        configured = true;
+    }
+    const int64_t tiles_i = (ni - 2 + JB_TI - 1) / JB_TI;
+    const int64_t tiles_j = (nj - 2 + JB_TJ - 1) / JB_TJ;
+    if (tr_hi < 0 || tr_hi > tiles_i) tr_hi = tiles_i;
+    if (tr_lo < 0) tr_lo = 0;
+    // grid.y is limited to 65535 tile rows per launch
+    for (int64_t t0 = tr_lo; t0 < tr_hi; t0 += 65535) {
+        const int64_t cnt = (tr_hi - t0 < 65535) ? (tr_hi - t0) : 65535;
+        dim3 grid((unsigned)tiles_j, (unsigned)cnt);
+        jacobi2d_block_kernel<<<grid, JB_THREADS, JB_SMEM, npb::st().stream>>>(
+            nsteps, (long long)ni, (long long)nj, src, dst, (long long)t0);
+        NPB_CHECK_LAUNCH("jacobi2d_block_kernel");
+        npb::count_launch();
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int npb_jacobi2d_tile_rows(void) { return JB_TI; }
+
+extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src,
+                                      double *dst, int64_t tile_row_lo, int64_t tile_row_hi) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nsteps >= 1 && nsteps <= NPB_JACOBI2D_MAX_BLOCK && (nsteps & 1), "npb_jacobi2d_block_f64",
+            "nsteps must be odd and in 1..7");
+    NPB_ARG(ni >= 0 && nj >= 0, "npb_jacobi2d_block_f64", "negative extent");
+    NPB_ARG(nj - 2 < (int64_t)JB_TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
+    if (ni < 3 || nj < 3) return 0;   // no interior
+    return launch_block(nsteps, ni, nj, src, dst, tile_row_lo, tile_row_hi);
+}
+
+extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(ni >= 0 && nj >= 0, "npb_jacobi2d_f64", "negative extent");
+    if (tsteps <= 1 || ni < 3 || nj < 3) return 0;   // range(1, TSTEPS) empty / no interior
+    // 2*(TSTEPS-1) sweeps.  The last one must be a single sweep B -> A so that
+    // B keeps state S-1 and A gets state S; the S-1 sweeps before it are split
+    // into an ODD number of ODD-sized blocked passes (A->B, B->A, ..., A->B).
+    const int64_t M = 2 * (tsteps - 1) - 1;
+    int64_t n = (M + NPB_JACOBI2D_MAX_BLOCK - 1) / NPB_JACOBI2D_MAX_BLOCK;
+    if ((n & 1) == 0) ++n;
+    int64_t extra_pairs = (M - n) / 2;            // distribute in units of 2 sweeps
+    const int64_t cap = (NPB_JACOBI2D_MAX_BLOCK - 1) / 2;
+    double *src = A, *dst = B;
+    for (int64_t p = 0; p < n; ++p) {
+        const int64_t left = n - p;
+        int64_t take = (extra_pairs + left - 1) / left;   // spread evenly
+        if (take > cap) take = cap;
+        extra_pairs -= take;
+        const int rc = launch_block((int)(1 + 2 * take), ni, nj, src, dst, 0, -1);
+        if (rc) return rc;
+        double *t = src; src = dst; dst = t;
+    }
+    // now src == B (state S-1), dst == A
+    return launch_block(1, ni, nj, src, dst, 0, -1);
+}

@@ -1,0 +1,66 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every
+symbol include/npb_b200.h declares, the ctypes prototypes cover exactly that set, and
+the product path fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "npb_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(npb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    from npbench_b200 import build
+    path = build.build()
+    cdll = ctypes.CDLL(path)
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(cdll, s), "libnpb_b200.so does not export %s" % s
+
+
+def test_ctypes_prototypes_match_header():
+    from npbench_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == header_symbols()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import npbench_b200 as nb
+    A = np.zeros((8, 8)); B = np.zeros((8, 8))
+    with pytest.raises(nb.B200Error, match="no CUDA device"):
+        nb.jacobi_2d(3, A, B)
+    with pytest.raises(nb.B200Error):
+        nb.DeviceArray.from_host(A)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "npbench_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
+                assert "liboracle" not in text, f
+
+
+def test_argument_validation_mirrors_numpy_errors():
+    import npbench_b200 as nb
+    with pytest.raises(ValueError):
+        nb.jacobi_2d(3, np.zeros((4, 4)), np.zeros((4, 5)))
+    with pytest.raises(ValueError):
+        nb.hdiff(np.zeros((8, 8, 3)), np.zeros((4, 4, 3)), np.zeros((4, 5, 3)))
+    with pytest.raises(IndexError):
+        nb.vadv(*(np.zeros((2, 2, 1)),) * 2, np.zeros((3, 2, 1)), *(np.zeros((2, 2, 1)),) * 2, 0.15)
+    with pytest.raises(TypeError):
+        nb.heat_3d(2, np.zeros((4, 4, 4), dtype=np.float32), np.zeros((4, 4, 4), dtype=np.float32))

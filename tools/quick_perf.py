@@ -1,0 +1,94 @@
+"""Quick device-timed throughput table for all kernels/presets (development aid, GPU only)."""
+import ctypes
+import json
+import sys
+import os
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import npbench_b200 as nb
+
+PRESETS = {
+    "jacobi_2d": {"S": (50, 150), "M": (80, 350), "L": (200, 700), "paper": (1000, 2800), "big": (21, 16384)},
+    "heat_3d": {"S": (25, 25), "M": (50, 40), "L": (100, 70), "paper": (500, 120), "big": (11, 640)},
+    "fdtd_2d": {"S": (20, 200, 220), "M": (60, 400, 450), "L": (150, 800, 900), "paper": (500, 1000, 1200),
+                "big": (10, 8192, 16384)},
+    "hdiff": {"S": (64, 64, 60), "M": (128, 128, 160), "L": (384, 384, 160), "paper": (256, 256, 160)},
+    "vadv": {"S": (60, 60, 40), "M": (112, 112, 80), "L": (180, 180, 160), "paper": (256, 256, 160)},
+}
+
+
+def timed(fn, reps, flush=True):
+    L = nb.lib()
+    ms = ctypes.c_float()
+    ts = []
+    for _ in range(3):
+        fn()
+    L.sync()
+    for _ in range(reps):
+        if flush:
+            L.l2_flush()
+        L.timer_start()
+        fn()
+        L.timer_stop(ctypes.byref(ms))
+        ts.append(ms.value)
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    nb.init(0)
+    L = nb.lib()
+    rng = np.random.default_rng(0)
+    rows = []
+    only = sys.argv[1:]
+    for bench, presets in PRESETS.items():
+        if only and bench not in only:
+            continue
+        for pname, p in presets.items():
+            if bench == "jacobi_2d":
+                ts, n = p
+                A = nb.DeviceArray((n, n)); B = nb.DeviceArray((n, n))
+                L.init_jacobi2d_f64(n, 0, n, n, A.ptr, B.ptr)
+                fn = lambda: nb.jacobi_2d(ts, A, B)
+                units = 2 * (ts - 1) * (n - 2) ** 2; bpu = 16
+            elif bench == "heat_3d":
+                ts, n = p
+                A = nb.DeviceArray((n, n, n)); B = nb.DeviceArray((n, n, n))
+                L.init_heat3d_f64(n, 0, n, A.ptr, B.ptr)
+                fn = lambda: nb.heat_3d(ts, A, B)
+                units = 2 * (ts - 1) * (n - 2) ** 3; bpu = 16
+            elif bench == "fdtd_2d":
+                tm, nx, ny = p
+                a = [nb.DeviceArray((nx, ny)) for _ in range(3)] + [nb.DeviceArray((tm,))]
+                L.init_fdtd2d_f64(tm, nx, ny, 0, nx, *(x.ptr for x in a))
+                fn = lambda: nb.fdtd_2d(tm, *a)
+                units = tm * nx * ny; bpu = 48
+            elif bench == "hdiff":
+                I, J, K = p
+                a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]
+                fn = lambda: nb.hdiff(*a)
+                units = I * J * K; bpu = 8.0 * ((I + 4) * (J + 4) + 2 * I * J) / (I * J)
+            else:
+                I, J, K = p
+                a = [nb.DeviceArray.from_host(rng.random(s)) for s in
+                     ((I, J, K), (I, J, K), (I + 1, J, K), (I, J, K), (I, J, K))]
+                fn = lambda: nb.vadv(*a, 0.15)
+                units = I * J * K; bpu = 8.0 * (6 * I + 1) / I
+            reps = 3 if pname in ("paper", "big") and bench in ("jacobi_2d", "heat_3d", "fdtd_2d") else 10
+            n0 = L.launch_count()
+            med, best = timed(fn, reps)
+            launches = (L.launch_count() - n0) // (reps + 3)
+            gc = units / (med * 1e-3) / 1e9
+            row = dict(bench=bench, preset=pname, params=p, ms=round(med, 4), best_ms=round(best, 4),
+                       gcell_s=round(gc, 2), eff_gbs=round(gc * bpu, 1), frac_6553=round(gc * bpu / 6553.6, 3),
+                       launches=int(launches))
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+            del fn
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/quick_perf.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
