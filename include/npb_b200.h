@@ -96,10 +96,13 @@ int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
 /* one fused time step on a row slab: local rows [0, nrows) are global rows
  * [row0, row0+nrows) of an nx_global-row grid; src fields -> dst fields
  * (out of place); `fict_t` is _fict_[t].  Rows whose stencil leaves the slab
- * are copied (they are ghost rows of the sharded driver). */
+ * are copied (they are ghost rows of the sharded driver).  Only local rows
+ * [row_lo, row_hi) are written (0, -1 for all): boundary rows first, interior
+ * overlapped with the halo exchange. */
 int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
                         const double *ex, const double *ey, const double *hz,
-                        double *ex_out, double *ey_out, double *hz_out, double fict_t);
+                        double *ex_out, double *ey_out, double *hz_out, double fict_t,
+                        int64_t row_lo, int64_t row_hi);
 
 /* hdiff(in_field, out_field, coeff): weather_stencils/hdiff/hdiff_numpy.py:5-29.
  * in (I+4, J+4, K); out, coeff (I, J, K). */

@@ -44,7 +44,7 @@ PROTOTYPES = {
     "npb_heat3d_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp]),
     "npb_heat3d_sweep_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _i64, _i64]),
     "npb_fdtd2d_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "npb_fdtd2d_step_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl]),
+    "npb_fdtd2d_step_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64]),
     "npb_hdiff_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp]),
     "npb_vadv_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _dbl]),
     "npb_jacobi2d_f64_host": (_int, [_i64, _i64, _i64, _vp, _vp]),

@@ -22,6 +22,7 @@ constexpr int FD_THREADS = 256;
 
 struct FdtdParams {
     long long nx_global, row0, nrows, ny;
+    long long r_lo, r_hi;     // local rows [r_lo, r_hi) are updated by this launch
     const double *ex, *ey, *hz;
     double *exo, *eyo, *hzo;
     const double *fict_ptr;   // if non-null, _fict_[t] is read from here
@@ -31,7 +32,7 @@ struct FdtdParams {
 __global__ void __launch_bounds__(FD_THREADS)
 fdtd2d_step_kernel(FdtdParams p) {
     const long long j = (long long)blockIdx.y * FD_THREADS + threadIdx.x;
-    const long long i = blockIdx.x;   // local row
+    const long long i = p.r_lo + blockIdx.x;   // local row
     if (j >= p.ny) return;
     const long long ny = p.ny;
     const long long gi = p.row0 + i;
@@ -65,10 +66,11 @@ fdtd2d_step_kernel(FdtdParams p) {
 }
 
 int launch_step(const FdtdParams &p) {
-    if (p.nrows <= 0 || p.ny <= 0) return 0;
+    const long long rows = p.r_hi - p.r_lo;
+    if (rows <= 0 || p.ny <= 0) return 0;
     const long long jb = (p.ny + FD_THREADS - 1) / FD_THREADS;
-    if (jb > 65535 || p.nrows >= (1LL << 31)) return npb::fail("fdtd2d", "grid too large");
-    dim3 grid((unsigned)p.nrows, (unsigned)jb);
+    if (jb > 65535 || rows >= (1LL << 31)) return npb::fail("fdtd2d", "grid too large");
+    dim3 grid((unsigned)rows, (unsigned)jb);
     fdtd2d_step_kernel<<<grid, FD_THREADS, 0, npb::st().stream>>>(p);
     NPB_CHECK_LAUNCH("fdtd2d_step_kernel");
     npb::count_launch();
@@ -79,11 +81,14 @@ int launch_step(const FdtdParams &p) {
 
 extern "C" int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
                                    const double *ex, const double *ey, const double *hz,
-                                   double *ex_out, double *ey_out, double *hz_out, double fict_t) {
+                                   double *ex_out, double *ey_out, double *hz_out, double fict_t,
+                                   int64_t row_lo, int64_t row_hi) {
     NPB_REQUIRE_INIT();
     NPB_ARG(nrows >= 0 && ny >= 0 && row0 >= 0 && row0 + nrows <= nx_global, "npb_fdtd2d_step_f64",
             "slab outside the grid");
-    FdtdParams p{nx_global, row0, nrows, ny, ex, ey, hz, ex_out, ey_out, hz_out, nullptr, fict_t};
+    if (row_lo < 0) row_lo = 0;
+    if (row_hi < 0 || row_hi > nrows) row_hi = nrows;
+    FdtdParams p{nx_global, row0, nrows, ny, row_lo, row_hi, ex, ey, hz, ex_out, ey_out, hz_out, nullptr, fict_t};
     return launch_step(p);
 }
 
@@ -100,7 +105,7 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
     for (int64_t t = 0; t < tmax; ++t) {
         double **s = (t & 1) ? w : u;
         double **d = (t & 1) ? u : w;
-        FdtdParams p{nx, 0, nx, ny, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
+        FdtdParams p{nx, 0, nx, ny, 0, nx, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
         const int rc = launch_step(p);
         if (rc) return rc;
     }

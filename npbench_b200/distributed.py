@@ -1,0 +1,270 @@
+"""Slab-sharded multi-GPU drivers: one process per GPU, halo exchange over NCCL/NVLink.
+
+The reference is single-device (no NCCL/MPI anywhere); this module is
+the B200 scale-out of its stencil family, launched with torchrun (one rank per GPU):
+
+  * jacobi_2d, heat_3d, fdtd_2d shard along the slowest axis (rows / i-planes are contiguous
+    in memory, so a halo is one contiguous block).  Every rank keeps `H` ghost rows on each
+    interior side and advances up to `H` sweeps between exchanges (the ghost zone absorbs the
+    contamination that creeps in one row per sweep), so the number of messages is
+    sweeps / H, not sweeps.  Exchanges are torch.distributed P2P batches (ncclSend/ncclRecv
+    inside one group) issued on a side stream as soon as the boundary rows of the last sweep
+    of a round are final; the interior of that sweep overlaps the transfer.
+  * hdiff and vadv shard along I with a fixed overlap (4 input rows / 1 wcon row) and need
+    no run-time exchange at all.
+
+The numerical work is delegated to an *engine*: `B200Engine` launches the CUDA kernels of
+libnpb_b200.so on torch CUDA tensors (torch is plumbing here: memory, streams, NCCL);
+tests substitute a CPU engine so that the decomposition/halo logic is covered with the
+gloo backend on machines without GPUs.  Results are bit-identical to the single-device
+kernels for any number of ranks.
+"""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+JACOBI_MAX_BLOCK = 7   # == NPB_JACOBI2D_MAX_BLOCK
+
+
+# --------------------------------------------------------------------------- partition
+def slab_bounds(n: int, size: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of an n-row grid owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(n, size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class Slab:
+    """Geometry of one rank's row slab with `H` ghost rows on interior sides."""
+
+    def __init__(self, n_global: int, size: int, rank: int, H: int):
+        self.n_global, self.size, self.rank, self.H = n_global, size, rank, H
+        self.lo, self.hi = slab_bounds(n_global, size, rank)
+        if size > 1 and (self.hi - self.lo) < H:
+            raise ValueError("slab of %d rows is thinner than the ghost depth %d" % (self.hi - self.lo, H))
+        self.ht = H if rank > 0 else 0            # ghost rows above
+        self.hb = H if rank < size - 1 else 0     # ghost rows below
+        self.row0 = self.lo - self.ht             # global index of local row 0
+        self.nloc = (self.hi - self.lo) + self.ht + self.hb
+
+    def owned(self, t: torch.Tensor) -> torch.Tensor:
+        return t[self.ht:self.nloc - self.hb]
+
+
+def jacobi_plan(total_sweeps: int, max_block: int = JACOBI_MAX_BLOCK) -> List[int]:
+    """Split S sweeps into odd-sized blocked passes, the last one a single sweep (see
+    csrc/jacobi2d.cu: npb_jacobi2d_f64 -- the same plan, so results and traffic match)."""
+    if total_sweeps <= 0:
+        return []
+    m = total_sweeps - 1
+    n = (m + max_block - 1) // max_block
+    if n % 2 == 0:
+        n += 1
+    extra, cap, plan = (m - n) // 2, (max_block - 1) // 2, []
+    for p in range(n):
+        left = n - p
+        take = min(cap, (extra + left - 1) // left)
+        extra -= take
+        plan.append(1 + 2 * take)
+    return plan + [1]
+
+
+# --------------------------------------------------------------------------- communication
+class HaloExchanger:
+    """Exchange H boundary rows of row-major slabs with rank-1 / rank+1."""
+
+    def __init__(self, slab: Slab, group=None):
+        self.slab, self.group = slab, group
+
+    def start(self, fields: Sequence[torch.Tensor]):
+        """Post sends of the outermost owned rows and receives into the ghost rows.
+        Returns the list of in-flight requests (empty on a single rank)."""
+        s, H, ops = self.slab, self.slab.H, []
+        for f in fields:
+            if s.ht:
+                ops.append(dist.P2POp(dist.isend, f[s.ht:s.ht + H], s.rank - 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, f[0:s.ht], s.rank - 1, self.group))
+            if s.hb:
+                ops.append(dist.P2POp(dist.isend, f[s.nloc - s.hb - H:s.nloc - s.hb], s.rank + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, f[s.nloc - s.hb:s.nloc], s.rank + 1, self.group))
+        return dist.batch_isend_irecv(ops) if ops else []
+
+    @staticmethod
+    def finish(reqs) -> None:
+        for r in reqs:
+            r.wait()
+
+
+# --------------------------------------------------------------------------- engines
+class B200Engine:
+    """Launches libnpb_b200.so kernels on torch CUDA tensors; two streams for overlap."""
+
+    def __init__(self, device: int):
+        from . import _lib
+        self.torch_device = torch.device("cuda", device)
+        torch.cuda.set_device(self.torch_device)
+        self.lib = _lib.init(device)
+        self.compute = torch.cuda.current_stream()
+        self.comm = torch.cuda.Stream()
+        self.lib.set_stream(self.compute.cuda_stream)
+        self.tile_rows = self.lib.jacobi2d_tile_rows()
+
+    def empty(self, *shape) -> torch.Tensor:
+        return torch.empty(*shape, dtype=torch.float64, device=self.torch_device)
+
+    # ---- kernels (all asynchronous on the compute stream)
+    def jacobi_block(self, nsteps, src, dst, t_lo, t_hi):
+        self.lib.jacobi2d_block_f64(nsteps, src.shape[0], src.shape[1], src.data_ptr(), dst.data_ptr(), t_lo, t_hi)
+
+    def heat_sweep(self, src, dst, i_lo, i_hi):
+        n0, n1, n2 = src.shape
+        self.lib.heat3d_sweep_f64(n0, n1, n2, src.data_ptr(), dst.data_ptr(), i_lo, i_hi)
+
+    def fdtd_step(self, nx_global, row0, src, dst, fict_t, r_lo, r_hi):
+        nrows, ny = src[0].shape
+        self.lib.fdtd2d_step_f64(nx_global, row0, nrows, ny, src[0].data_ptr(), src[1].data_ptr(),
+                                 src[2].data_ptr(), dst[0].data_ptr(), dst[1].data_ptr(), dst[2].data_ptr(),
+                                 float(fict_t), r_lo, r_hi)
+
+    def hdiff(self, inf, out, coeff):
+        I, J, K = out.shape
+        self.lib.hdiff_f64(I, J, K, inf.data_ptr(), out.data_ptr(), coeff.data_ptr())
+
+    def vadv(self, us, u, w, up, ut, dtr):
+        I, J, K = us.shape
+        self.lib.vadv_f64(I, J, K, us.data_ptr(), u.data_ptr(), w.data_ptr(), up.data_ptr(), ut.data_ptr(), float(dtr))
+
+    def copy(self, dst, src):
+        dst.copy_(src)
+
+    # ---- stream choreography
+    def boundary_done(self):
+        ev = torch.cuda.Event()
+        ev.record(self.compute)
+        return ev
+
+    def start_exchange(self, exchanger: HaloExchanger, fields, after):
+        """Issue the P2P batch on the comm stream once event `after` has fired."""
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(after)
+            return exchanger.start(fields)
+
+    def finish_exchange(self, reqs):
+        # req.wait() makes the *current* (compute) stream wait for the NCCL work
+        HaloExchanger.finish(reqs)
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.torch_device)
+
+
+# --------------------------------------------------------------------------- drivers
+def _boundary_tile_ranges(slab: Slab, tile_rows: int) -> Tuple[int, int, int]:
+    """Tile-row split for the blocked jacobi pass on a local slab: tile rows [0, tb) and
+    [te, ntr) hold every ghost row and every row that is sent; [tb, te) is the interior."""
+    ntr = (slab.nloc - 2 + tile_rows - 1) // tile_rows
+    tb = 0
+    if slab.ht:
+        tb = min(ntr, (slab.ht + slab.H - 2) // tile_rows + 1)          # covers rows 1 .. ht+H-1
+    te = ntr
+    if slab.hb:
+        te = max(tb, (slab.nloc - slab.hb - slab.H - 1) // tile_rows)   # first tile with row nloc-hb-H
+    return tb, te, ntr
+
+
+def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None) -> None:
+    """kernel(TSTEPS, A, B) of jacobi_2d_numpy.py:4-10 on a row slab.  A, B are the local
+    (slab.nloc, ncols) arrays INCLUDING ghost rows, initialised consistently with the global
+    grid (ghost rows hold the neighbour's rows).  On return the owned rows of A and B equal
+    the corresponding rows of the single-device result, bit for bit."""
+    assert slab.H >= JACOBI_MAX_BLOCK or slab.size == 1
+    ex = HaloExchanger(slab, group)
+    tb, te, ntr = _boundary_tile_ranges(slab, engine.tile_rows)
+    src, dst = A, B
+    for n in jacobi_plan(2 * (TSTEPS - 1)):
+        if slab.size == 1:
+            engine.jacobi_block(n, src, dst, 0, ntr)
+        else:
+            if tb > 0:
+                engine.jacobi_block(n, src, dst, 0, tb)
+            if te < ntr:
+                engine.jacobi_block(n, src, dst, te, ntr)
+            reqs = engine.start_exchange(ex, [dst], engine.boundary_done())
+            if te > tb:
+                engine.jacobi_block(n, src, dst, tb, te)     # overlaps the halo transfer
+            engine.finish_exchange(reqs)
+        src, dst = dst, src
+
+
+def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None) -> None:
+    """kernel(TSTEPS, A, B) of heat_3d_numpy.py:4-20 on an i-plane slab (ghost depth slab.H)."""
+    ex = HaloExchanger(slab, group)
+    total = 2 * (TSTEPS - 1)
+    src, dst, done, H, n = A, B, 0, slab.H, slab.nloc
+    while done < total:
+        k = min(H, total - done) if slab.size > 1 else total - done
+        for s in range(k):
+            last = (s == k - 1) and slab.size > 1
+            if not last:
+                engine.heat_sweep(src, dst, 1, n - 1)
+            else:
+                b_lo = (slab.ht + H) if slab.ht else 1            # planes [1, b_lo) feed the upward send
+                b_hi = (n - slab.hb - H) if slab.hb else n - 1    # planes [b_hi, n-1) feed the downward send
+                b_lo = min(b_lo, n - 1); b_hi = max(b_hi, b_lo)
+                if b_lo > 1:
+                    engine.heat_sweep(src, dst, 1, b_lo)
+                if b_hi < n - 1:
+                    engine.heat_sweep(src, dst, b_hi, n - 1)
+                reqs = engine.start_exchange(ex, [dst], engine.boundary_done())
+                if b_hi > b_lo:
+                    engine.heat_sweep(src, dst, b_lo, b_hi)
+                engine.finish_exchange(reqs)
+            src, dst = dst, src
+        done += k
+    # The array that was NOT written last holds state total-1 with ghost rows one round
+    # stale -- irrelevant: only owned rows are results.
+
+
+def fdtd_2d_sharded(engine, slab: Slab, TMAX: int, ex_: torch.Tensor, ey: torch.Tensor, hz: torch.Tensor,
+                    fict: Sequence[float], group=None) -> None:
+    """kernel(TMAX, ex, ey, hz, _fict_) of fdtd_2d_numpy.py:4-11 on a row slab.  `fict` is a
+    host sequence (the reference indexes _fict_[t] on the host too)."""
+    exch = HaloExchanger(slab, group)
+    user = [ex_, ey, hz]
+    work = [engine.empty(*f.shape) for f in user]
+    src, dst, t, H, n = user, work, 0, slab.H, slab.nloc
+    while t < TMAX:
+        k = min(H, TMAX - t) if slab.size > 1 else TMAX - t
+        for s in range(k):
+            last = (s == k - 1) and slab.size > 1
+            f_t = float(fict[t + s])
+            if not last:
+                engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, n)
+            else:
+                b_lo = min(n, slab.ht + H) if slab.ht else 0
+                b_hi = max(b_lo, n - slab.hb - H) if slab.hb else n
+                if b_lo > 0:
+                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, b_lo)
+                if b_hi < n:
+                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_hi, n)
+                reqs = engine.start_exchange(exch, dst, engine.boundary_done())
+                if b_hi > b_lo:
+                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_lo, b_hi)
+                engine.finish_exchange(reqs)
+            src, dst = dst, src
+        t += k
+    if src is not user:          # an odd number of steps leaves the result in the workspace
+        for u, w in zip(user, src):
+            engine.copy(u, w)
+
+
+# --------------------------------------------------------------------------- halo-free shards
+def hdiff_shard(I: int, size: int, rank: int) -> Tuple[int, int]:
+    """Output rows [lo, hi) of rank; it needs in_field[lo : hi + 4] (fixed 4-row overlap,
+    hdiff_numpy.py:7-28) and coeff/out_field[lo:hi]."""
+    return slab_bounds(I, size, rank)
+
+
+def vadv_shard(I: int, size: int, rank: int) -> Tuple[int, int]:
+    """Rows [lo, hi) of rank; wcon needs rows [lo : hi + 1] (vadv_numpy.py:16, 33-34)."""
+    return slab_bounds(I, size, rank)

@@ -1,0 +1,172 @@
+"""Host-side logic of the slab-sharded drivers (npbench_b200/distributed.py) on CPU.
+
+world_size 2 and 3, gloo backend, 127.0.0.1.  The CUDA engine is replaced by a CPU engine
+that computes each local operation with the oracle and POISONS (NaN) everything the CUDA
+kernels leave undefined on ghost rows, so any leak of ghost garbage into owned rows, a
+missing exchange or a wrong tile/row range shows up as a bit mismatch against the
+single-domain oracle result.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from npbench_b200 import distributed as D
+
+
+class CpuEngine:
+    tile_rows = 4          # small tiles => many boundary/interior splits
+
+    def empty(self, *shape):
+        return torch.full(shape, float("nan"), dtype=torch.float64)
+
+    def jacobi_block(self, n, src, dst, t_lo, t_hi):
+        a, b = src.numpy().copy(), dst.numpy().copy()
+        oracle.jacobi_2d_sweeps(n, a, b)
+        res = b if n % 2 else a
+        r0, r1 = 1 + t_lo * self.tile_rows, min(src.shape[0] - 1, 1 + t_hi * self.tile_rows)
+        dst.numpy()[r0:r1, 1:-1] = res[r0:r1, 1:-1]
+
+    def heat_sweep(self, src, dst, i_lo, i_hi):
+        a, b = src.numpy().copy(), dst.numpy().copy()
+        oracle.heat_3d_sweeps(1, a, b)
+        i_lo, i_hi = max(1, i_lo), min(src.shape[0] - 1, i_hi)
+        dst.numpy()[i_lo:i_hi, 1:-1, 1:-1] = b[i_lo:i_hi, 1:-1, 1:-1]
+
+    def fdtd_step(self, nx_global, row0, src, dst, fict_t, r_lo, r_hi):
+        f = [x.numpy().copy() for x in src]
+        n = f[0].shape[0]
+        oracle.fdtd_2d(1, f[0], f[1], f[2], np.array([fict_t]))
+        if row0 > 0:                      # ghost row: no row above -> undefined in the CUDA contract
+            f[1][0] = np.nan; f[2][0] = np.nan
+        if row0 + n < nx_global:          # ghost row: no row below
+            f[2][n - 1] = np.nan
+        r_hi = n if r_hi < 0 else r_hi
+        for d, x in zip(dst, f):
+            d.numpy()[r_lo:r_hi] = x[r_lo:r_hi]
+
+    def copy(self, dst, src):
+        dst.copy_(src)
+
+    def boundary_done(self):
+        return None
+
+    def start_exchange(self, exchanger, fields, after):
+        return exchanger.start(fields)
+
+    def finish_exchange(self, reqs):
+        D.HaloExchanger.finish(reqs)
+
+
+def _local(slab, full):
+    return torch.from_numpy(np.ascontiguousarray(full[slab.row0:slab.row0 + slab.nloc]).copy())
+
+
+def _worker(rank, size, port, case):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        eng = CpuEngine()
+        rng = np.random.default_rng(1234)          # same stream on every rank
+        if case == "jacobi":
+            for ts, (ni, nj) in ((2, (40, 13)), (6, (61, 30)), (12, (47, 19))):
+                A, B = rng.random((ni, nj)), rng.random((ni, nj))
+                slab = D.Slab(ni, size, rank, D.JACOBI_MAX_BLOCK)
+                lA, lB = _local(slab, A), _local(slab, B)
+                D.jacobi_2d_sharded(eng, slab, ts, lA, lB)
+                oracle.jacobi_2d(ts, A, B)
+                assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank)
+                assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank)
+        elif case == "heat":
+            for ts, shape, H in ((2, (14, 6, 7), 3), (5, (17, 5, 6), 4), (8, (25, 6, 5), 3)):
+                A, B = rng.random(shape), rng.random(shape)
+                slab = D.Slab(shape[0], size, rank, H)
+                lA, lB = _local(slab, A), _local(slab, B)
+                D.heat_3d_sharded(eng, slab, ts, lA, lB)
+                oracle.heat_3d(ts, A, B)
+                assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank)
+                assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank)
+        elif case == "fdtd":
+            for tm, (nx, ny), H in ((1, (12, 9), 2), (7, (23, 11), 3), (10, (30, 8), 4), (4, (19, 5), 5)):
+                ex, ey, hz = rng.random((nx, ny)), rng.random((nx, ny)), rng.random((nx, ny))
+                fict = rng.random(tm)
+                slab = D.Slab(nx, size, rank, H)
+                l = [_local(slab, f) for f in (ex, ey, hz)]
+                D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict)
+                oracle.fdtd_2d(tm, ex, ey, hz, fict)
+                for name, got, want in zip(("ex", "ey", "hz"), l, (ex, ey, hz)):
+                    assert np.array_equal(slab.owned(got).numpy(), want[slab.lo:slab.hi]), (name, tm, rank)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("size", [2, 3])
+@pytest.mark.parametrize("case", ["jacobi", "heat", "fdtd"])
+def test_sharded_equals_single_domain(case, size):
+    mp.spawn(_worker, args=(size, _free_port(), case), nprocs=size, join=True)
+
+
+def test_single_rank_driver_equals_kernel():
+    """size == 1: no process group needed, the driver degenerates to the plain kernel."""
+    eng = CpuEngine()
+    rng = np.random.default_rng(5)
+    A, B = rng.random((21, 17)), rng.random((21, 17))
+    slab = D.Slab(21, 1, 0, D.JACOBI_MAX_BLOCK)
+    lA, lB = torch.from_numpy(A.copy()), torch.from_numpy(B.copy())
+    D.jacobi_2d_sharded(eng, slab, 9, lA, lB)
+    oracle.jacobi_2d(9, A, B)
+    assert np.array_equal(lA.numpy(), A) and np.array_equal(lB.numpy(), B)
+
+
+def test_plan_matches_the_c_driver_rules():
+    for ts in range(1, 60):
+        plan = D.jacobi_plan(2 * (ts - 1))
+        assert sum(plan) == 2 * (ts - 1)
+        assert all(p % 2 == 1 and 1 <= p <= 7 for p in plan)
+        assert len(plan) % 2 == 0 and (not plan or plan[-1] == 1)
+
+
+def test_slab_bounds_cover_without_overlap():
+    for n in (7, 64, 1000):
+        for size in (1, 2, 3, 8):
+            b = [D.slab_bounds(n, size, r) for r in range(size)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(size - 1))
+
+
+@pytest.mark.parametrize("size", [2, 4])
+def test_halo_free_shards_of_hdiff_and_vadv(size):
+    I, J, K = 13, 6, 5
+    inf, outf, coeff = oracle.init_hdiff(I, J, K)
+    want = outf.copy(); oracle.hdiff(inf, want, coeff)
+    parts = []
+    for r in range(size):
+        lo, hi = D.hdiff_shard(I, size, r)
+        o = np.empty((hi - lo, J, K))
+        oracle.hdiff(np.ascontiguousarray(inf[lo:hi + 4]), o, np.ascontiguousarray(coeff[lo:hi]))
+        parts.append(o)
+    assert np.array_equal(np.concatenate(parts), want)
+    dtr, us, u, w, up, ut = oracle.init_vadv(I, J, K)
+    want = us.copy(); oracle.vadv(want, u, w, up, ut, dtr)
+    parts = []
+    for r in range(size):
+        lo, hi = D.vadv_shard(I, size, r)
+        o = np.ascontiguousarray(us[lo:hi]).copy()
+        oracle.vadv(o, *(np.ascontiguousarray(x[lo:hi]) for x in (u,)), np.ascontiguousarray(w[lo:hi + 1]),
+                    np.ascontiguousarray(up[lo:hi]), np.ascontiguousarray(ut[lo:hi]), dtr)
+        parts.append(o)
+    assert np.array_equal(np.concatenate(parts), want)
