@@ -19,6 +19,7 @@ tests substitute a CPU engine so that the decomposition/halo logic is covered wi
 gloo backend on machines without GPUs.  Results are bit-identical to the single-device
 kernels for any number of ranks.
 """
+import threading
 from typing import List, Sequence, Tuple
 
 import torch
@@ -100,12 +101,17 @@ class HaloExchanger:
 class B200Engine:
     """Launches libnpb_b200.so kernels on torch CUDA tensors; two streams for overlap."""
 
+    _launch_lock = threading.Lock()   # the library's current stream is process global
+
     def __init__(self, device: int):
         from . import _lib
         self.torch_device = torch.device("cuda", device)
         torch.cuda.set_device(self.torch_device)
         self.lib = _lib.init(device)
-        self.compute = torch.cuda.current_stream()
+        # a dedicated compute stream shared by torch and the library (handle 0 -- torch's legacy
+        # default stream -- means "library stream" to npb_set_stream, so never pass that one)
+        self.compute = torch.cuda.Stream()
+        torch.cuda.set_stream(self.compute)
         self.comm = torch.cuda.Stream()
         self.lib.set_stream(self.compute.cuda_stream)
         self.tile_rows = self.lib.jacobi2d_tile_rows()
@@ -114,26 +120,34 @@ class B200Engine:
         return torch.empty(*shape, dtype=torch.float64, device=self.torch_device)
 
     # ---- kernels (all asynchronous on the compute stream)
+    def _launch(self, fn, *args):
+        # (re)bind the library to this engine's compute stream and enqueue, atomically
+        with B200Engine._launch_lock:
+            self.lib.set_stream(self.compute.cuda_stream)
+            fn(*args)
+
     def jacobi_block(self, nsteps, src, dst, t_lo, t_hi):
-        self.lib.jacobi2d_block_f64(nsteps, src.shape[0], src.shape[1], src.data_ptr(), dst.data_ptr(), t_lo, t_hi)
+        self._launch(self.lib.jacobi2d_block_f64, nsteps, src.shape[0], src.shape[1], src.data_ptr(),
+                     dst.data_ptr(), t_lo, t_hi)
 
     def heat_sweep(self, src, dst, i_lo, i_hi):
         n0, n1, n2 = src.shape
-        self.lib.heat3d_sweep_f64(n0, n1, n2, src.data_ptr(), dst.data_ptr(), i_lo, i_hi)
+        self._launch(self.lib.heat3d_sweep_f64, n0, n1, n2, src.data_ptr(), dst.data_ptr(), i_lo, i_hi)
 
     def fdtd_step(self, nx_global, row0, src, dst, fict_t, r_lo, r_hi):
         nrows, ny = src[0].shape
-        self.lib.fdtd2d_step_f64(nx_global, row0, nrows, ny, src[0].data_ptr(), src[1].data_ptr(),
-                                 src[2].data_ptr(), dst[0].data_ptr(), dst[1].data_ptr(), dst[2].data_ptr(),
-                                 float(fict_t), r_lo, r_hi)
+        self._launch(self.lib.fdtd2d_step_f64, nx_global, row0, nrows, ny, src[0].data_ptr(), src[1].data_ptr(),
+                     src[2].data_ptr(), dst[0].data_ptr(), dst[1].data_ptr(), dst[2].data_ptr(),
+                     float(fict_t), r_lo, r_hi)
 
     def hdiff(self, inf, out, coeff):
         I, J, K = out.shape
-        self.lib.hdiff_f64(I, J, K, inf.data_ptr(), out.data_ptr(), coeff.data_ptr())
+        self._launch(self.lib.hdiff_f64, I, J, K, inf.data_ptr(), out.data_ptr(), coeff.data_ptr())
 
     def vadv(self, us, u, w, up, ut, dtr):
         I, J, K = us.shape
-        self.lib.vadv_f64(I, J, K, us.data_ptr(), u.data_ptr(), w.data_ptr(), up.data_ptr(), ut.data_ptr(), float(dtr))
+        self._launch(self.lib.vadv_f64, I, J, K, us.data_ptr(), u.data_ptr(), w.data_ptr(), up.data_ptr(),
+                     ut.data_ptr(), float(dtr))
 
     def copy(self, dst, src):
         dst.copy_(src)
@@ -172,13 +186,14 @@ def _boundary_tile_ranges(slab: Slab, tile_rows: int) -> Tuple[int, int, int]:
     return tb, te, ntr
 
 
-def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None) -> None:
+def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None,
+                      exchanger=None) -> None:
     """kernel(TSTEPS, A, B) of jacobi_2d_numpy.py:4-10 on a row slab.  A, B are the local
     (slab.nloc, ncols) arrays INCLUDING ghost rows, initialised consistently with the global
     grid (ghost rows hold the neighbour's rows).  On return the owned rows of A and B equal
     the corresponding rows of the single-device result, bit for bit."""
     assert slab.H >= JACOBI_MAX_BLOCK or slab.size == 1
-    ex = HaloExchanger(slab, group)
+    ex = exchanger or HaloExchanger(slab, group)
     tb, te, ntr = _boundary_tile_ranges(slab, engine.tile_rows)
     src, dst = A, B
     for n in jacobi_plan(2 * (TSTEPS - 1)):
@@ -196,9 +211,10 @@ def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch
         src, dst = dst, src
 
 
-def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None) -> None:
+def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None,
+                    exchanger=None) -> None:
     """kernel(TSTEPS, A, B) of heat_3d_numpy.py:4-20 on an i-plane slab (ghost depth slab.H)."""
-    ex = HaloExchanger(slab, group)
+    ex = exchanger or HaloExchanger(slab, group)
     total = 2 * (TSTEPS - 1)
     src, dst, done, H, n = A, B, 0, slab.H, slab.nloc
     while done < total:
@@ -226,10 +242,10 @@ def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.T
 
 
 def fdtd_2d_sharded(engine, slab: Slab, TMAX: int, ex_: torch.Tensor, ey: torch.Tensor, hz: torch.Tensor,
-                    fict: Sequence[float], group=None) -> None:
+                    fict: Sequence[float], group=None, exchanger=None) -> None:
     """kernel(TMAX, ex, ey, hz, _fict_) of fdtd_2d_numpy.py:4-11 on a row slab.  `fict` is a
     host sequence (the reference indexes _fict_[t] on the host too)."""
-    exch = HaloExchanger(slab, group)
+    exch = exchanger or HaloExchanger(slab, group)
     user = [ex_, ey, hz]
     work = [engine.empty(*f.shape) for f in user]
     src, dst, t, H, n = user, work, 0, slab.H, slab.nloc

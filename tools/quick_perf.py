@@ -43,9 +43,11 @@ def main():
     rows = []
     only = sys.argv[1:]
     for bench, presets in PRESETS.items():
-        if only and bench not in only:
+        if only and not any(o.split(":")[0] == bench for o in only):
             continue
         for pname, p in presets.items():
+            if only and not any(o == bench or o == bench + ":" + pname for o in only):
+                continue
             if bench == "jacobi_2d":
                 ts, n = p
                 A = nb.DeviceArray((n, n)); B = nb.DeviceArray((n, n))
