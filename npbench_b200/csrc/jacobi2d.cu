@@ -28,6 +28,8 @@ constexpr int JB_TI = 32;                      // output rows per tile
 constexpr int JB_R = JB_TI + 2 * NPB_JACOBI2D_MAX_BLOCK;   // 46 shared tile rows
 constexpr int JB_THREADS = 256;
 constexpr int JB_SEGS = JB_THREADS / (JB_C / 2);           // 4 row segments
+constexpr int JB_LD = (JB_R * JB_C) / JB_THREADS;          // 23 tile elements per thread
+static_assert(JB_LD * JB_THREADS == JB_R * JB_C, "tile must divide evenly over the threads");
 constexpr size_t JB_SMEM = (size_t)2 * JB_R * JB_C * sizeof(double);   // 94208 B
 
 __global__ void __launch_bounds__(JB_THREADS, 2)
@@ -46,13 +48,28 @@ jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__re
     // ---- load: rows [i0-h, i0+TI+h), cols [j0-h, j0+TJ+h), clipped to the grid
     const long long r_lo = max(0LL, i0 - h), r_hi = min(ni - 1, i0 + JB_TI - 1 + h);
     const long long c_lo = max(0LL, j0 - h), c_hi = min(nj - 1, j0 + JB_TJ - 1 + h);
-    for (int idx = threadIdx.x; idx < JB_R * JB_C; idx += JB_THREADS) {
-        const int r = idx / JB_C, c = idx % JB_C;
-        const long long gi = gi_base + r, gj = gj_base + c;
-        if (gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi) {
-            buf0[idx] = __ldg(src + gi * nj + gj);
-            if (gi == 0 || gi == ni - 1 || gj == 0 || gj == nj - 1)
-                buf1[idx] = __ldg((const double *)dst + gi * nj + gj);   // dst's own constant border
+    // All JB_LD loads of a thread are issued before the first shared store, so ~23 x 8 B per
+    // thread are in flight (the load phase was global-latency bound when unrolled only x4).
+    {
+        double v[JB_LD];
+#pragma unroll
+        for (int u = 0; u < JB_LD; ++u) {
+            const int idx = threadIdx.x + u * JB_THREADS;
+            const int r = idx / JB_C, c = idx % JB_C;
+            const long long gi = gi_base + r, gj = gj_base + c;
+            const bool in = gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi;
+            v[u] = in ? __ldg(src + gi * nj + gj) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < JB_LD; ++u) {
+            const int idx = threadIdx.x + u * JB_THREADS;
+            const int r = idx / JB_C, c = idx % JB_C;
+            const long long gi = gi_base + r, gj = gj_base + c;
+            if (gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi) {
+                buf0[idx] = v[u];
+                if (gi == 0 || gi == ni - 1 || gj == 0 || gj == nj - 1)
+                    buf1[idx] = __ldg((const double *)dst + gi * nj + gj);   // dst's own constant border
+            }
         }
     }
     __syncthreads();

@@ -32,6 +32,9 @@
 
 namespace {
 
+constexpr int VA_U = 6;    // phase-A work items loaded per batch
+constexpr int VD_U = 10;   // phase-D work items loaded per batch
+
 struct VadvParams {
     long long ncols;      // I*J
     int K;
@@ -56,43 +59,50 @@ vadv_warp_kernel(VadvParams p) {
     const long long JK = (long long)p.J * K;
 
     // ---------------- phase A: lanes along k ------------------------------
-    for (int cc = 0; cc < nc; ++cc) {
-        const long long base = (col0 + cc) * K;
-        const double *us = p.u_stage + base;
-        const double *w0 = p.wcon + base;          // wcon[i  , j, :]
-        const double *w1 = p.wcon + base + JK;     // wcon[i+1, j, :]
-        const double *up = p.u_pos + base;
-        const double *ut = p.utens + base;
-        const double *uo = p.utens_stage + base;
-        for (int k = lane; k < K; k += 32) {
-            const double u_c = __ldg(us + k);
-            const double upk = ldg_stream(up + k);
-            const double utk = ldg_stream(ut + k);
-            const double uok = ldg_stream(uo + k);
-            // vadv_numpy.py:24-25 / 47-48 / 63-64
-            const double d0 = (dtr * upk + utk) + uok;
-            double a = 0.0, corr;
-            if (k == 0) {
-                // :16-23   gcv = 0.25*(wcon[i+1,k+1]+wcon[i,k+1]); cs = gcv*BET_M
-                const double gcv = 0.25 * (__ldg(w1 + 1) + __ldg(w0 + 1));
-                const double cs = gcv * 0.5;
-                corr = (-cs) * (__ldg(us + 1) - u_c);
-            } else {
-                // :33,36,39 / :56-58   gav = -0.25*(wcon[i+1,k]+wcon[i,k]); as = acol = gav*0.5
-                const double gav = -0.25 * (__ldg(w1 + k) + __ldg(w0 + k));
-                a = gav * 0.5;
-                const double t_lo = (-a) * (__ldg(us + k - 1) - u_c);
-                if (k < K - 1) {
-                    // :34,37,44-46
-                    const double gcv = 0.25 * (__ldg(w1 + k + 1) + __ldg(w0 + k + 1));
-                    const double cs = gcv * 0.5;
-                    corr = t_lo - (cs * (__ldg(us + k + 1) - u_c));
-                } else {
-                    corr = t_lo;   // :62
-                }
+    // Work items = (column, 32-level block); VA_U items are loaded as one batch so that
+    // ~10*VA_U independent loads per lane are in flight (the warp is alone in its CTA, so
+    // memory-level parallelism has to come from the instruction stream).  Neighbour
+    // levels use clamped indices and selects instead of branches.
+    const int nkb = (K + 31) >> 5;
+    const int items = nc * nkb;
+    for (int it0 = 0; it0 < items; it0 += VA_U) {
+        double r_um[VA_U], r_uc[VA_U], r_un[VA_U], r_wc[VA_U], r_wn[VA_U], r_d0a[VA_U], r_ut[VA_U], r_uo[VA_U];
+        int r_k[VA_U], r_cc[VA_U];
+#pragma unroll
+        for (int u = 0; u < VA_U; ++u) {
+            const int it = min(it0 + u, items - 1);
+            const int cc = it / nkb;
+            const int k = min(((it - cc * nkb) << 5) + lane, K - 1);
+            const int km = max(k - 1, 0), kp = min(k + 1, K - 1);
+            const long long base = (col0 + cc) * K;
+            r_k[u] = k; r_cc[u] = cc;
+            r_um[u] = __ldg(p.u_stage + base + km);
+            r_uc[u] = __ldg(p.u_stage + base + k);
+            r_un[u] = __ldg(p.u_stage + base + kp);
+            // wcon[i+1,j,k] + wcon[i,j,k]   (vadv_numpy.py:16,33,34,56)
+            r_wc[u] = __ldg(p.wcon + base + JK + k) + __ldg(p.wcon + base + k);
+            r_wn[u] = __ldg(p.wcon + base + JK + kp) + __ldg(p.wcon + base + kp);
+            r_d0a[u] = ldg_stream(p.u_pos + base + k);
+            r_ut[u] = ldg_stream(p.utens + base + k);
+            r_uo[u] = ldg_stream(p.utens_stage + base + k);
+        }
+#pragma unroll
+        for (int u = 0; u < VA_U; ++u) {
+            const int k = r_k[u];
+            // :24-25 / :47-48 / :63-64
+            const double d0 = (dtr * r_d0a[u] + r_ut[u]) + r_uo[u];
+            // :33,36,39   gav = -0.25*w_k ; as = acol = gav*0.5      (unused at k = 0)
+            const double a = (-0.25 * r_wc[u]) * 0.5;
+            // :16-17 / :34,37   gcv = 0.25*w_{k+1} ; cs = gcv*0.5     (unused at k = K-1)
+            const double cs = (0.25 * r_wn[u]) * 0.5;
+            const double t_lo = (-a) * (r_um[u] - r_uc[u]);
+            const double t_hi = cs * (r_un[u] - r_uc[u]);
+            // :23 (-cs)*(...) == -(cs*(...)) exactly ; :44-46 ; :62
+            const double corr = (k == 0) ? -t_hi : ((k < K - 1) ? (t_lo - t_hi) : t_lo);
+            if (it0 + u < items && ((it0 + u - r_cc[u] * nkb) << 5) + lane < K) {
+                tA[k * NCP + r_cc[u]] = a;
+                tD[k * NCP + r_cc[u]] = d0 + corr;
             }
-            tA[k * NCP + cc] = a;
-            tD[k * NCP + cc] = d0 + corr;
         }
     }
     __syncwarp();
@@ -102,67 +112,88 @@ vadv_warp_kernel(VadvParams p) {
         double *cA = tA + lane;
         double *cD = tD + lane;
         // k = 0 : vadv_numpy.py:19-30   ccol = gcv*BET_P == -a_1
-        double a_next = cA[NCP];
-        double ccv = -a_next;
+        double a_cur = cA[NCP];                              // a_1
+        double a_nxt = cA[min(2, K - 1) * NCP];              // a_2
+        double dc_cur = cD[min(1, K - 1) * NCP];             // dc_1
+        double ccv = -a_cur;
         double bcol = dtr - ccv;
         double divided = 1.0 / bcol;
         double c_prev = ccv * divided;
         double d_prev = cD[0] * divided;
         cA[0] = c_prev;
         cD[0] = d_prev;
-        // 1 <= k <= K-2 : :32-53
+        // 1 <= k <= K-2 : :32-53.  Operands of level k+1 are fetched before the stores of
+        // level k, so their shared-memory latency hides under the divide chain.
         for (int k = 1; k < K - 1; ++k) {
-            const double a = a_next;
-            a_next = cA[(k + 1) * NCP];
-            ccv = -a_next;
+            const double a_pf = cA[min(k + 2, K - 1) * NCP];
+            const double dc_pf = cD[(k + 1) * NCP];
+            const double a = a_cur;
+            ccv = -a_nxt;
             bcol = (dtr - a) - ccv;
             divided = 1.0 / (bcol - c_prev * a);
-            const double dc = cD[k * NCP];
             c_prev = ccv * divided;
-            d_prev = (dc - d_prev * a) * divided;
+            d_prev = (dc_cur - d_prev * a) * divided;
             cA[k * NCP] = c_prev;
             cD[k * NCP] = d_prev;
+            a_cur = a_nxt; a_nxt = a_pf; dc_cur = dc_pf;
         }
         {   // k = K-1 : :55-68
-            const int k = K - 1;
-            const double a = a_next;
+            const double a = a_cur;
             bcol = dtr - a;
             divided = 1.0 / (bcol - c_prev * a);
-            d_prev = (cD[k * NCP] - d_prev * a) * divided;
-            cD[k * NCP] = d_prev;       // datacol_{K-1} = dcol_{K-1}  (:70-73)
+            d_prev = (dc_cur - d_prev * a) * divided;
+            cD[(K - 1) * NCP] = d_prev;       // datacol_{K-1} = dcol_{K-1}  (:70-73)
         }
         // back-substitution : :75-78
         double x = d_prev;
+        double c_k = (K >= 2) ? cA[(K - 2) * NCP] : 0.0, d_k = cD[(K - 2) * NCP];
         for (int k = K - 2; k >= 0; --k) {
-            x = cD[k * NCP] - cA[k * NCP] * x;
+            const int kn = max(k - 1, 0);
+            const double c_pf = cA[kn * NCP], d_pf = cD[kn * NCP];
+            x = d_k - c_k * x;
             cD[k * NCP] = x;
+            c_k = c_pf; d_k = d_pf;
         }
     }
     __syncwarp();
 
     // ---------------- phase D: lanes along k ------------------------------
-    for (int cc = 0; cc < nc; ++cc) {
-        const long long base = (col0 + cc) * K;
-        const double *up = p.u_pos + base;
-        double *uo = p.utens_stage + base;
-        for (int k = lane; k < K; k += 32)
-            stg_stream(uo + k, dtr * (tD[k * NCP + cc] - __ldg(up + k)));   // :73, :78
+    for (int it0 = 0; it0 < items; it0 += VD_U) {
+        double r_up[VD_U];
+#pragma unroll
+        for (int u = 0; u < VD_U; ++u) {
+            const int it = min(it0 + u, items - 1);
+            const int cc = it / nkb;
+            const int k = min(((it - cc * nkb) << 5) + lane, K - 1);
+            r_up[u] = __ldg(p.u_pos + (col0 + cc) * K + k);
+        }
+#pragma unroll
+        for (int u = 0; u < VD_U; ++u) {
+            const int it = it0 + u;
+            const int cc = min(it, items - 1) / nkb;
+            const int k = ((it - cc * nkb) << 5) + lane;
+            if (it < items && k < K)
+                stg_stream(p.utens_stage + (col0 + cc) * K + k, dtr * (tD[k * NCP + cc] - r_up[u]));   // :73, :78
+        }
     }
 }
 
-// Pick NC (columns per single-warp CTA) maximising resident columns per SM.
+// Pick NC (columns per single-warp CTA).  The forward sweep is a serial divide chain per
+// column; one warp per SM sub-partition already keeps the FP64 pipe ~85% busy, so the goal
+// is to maximise columns resident on up to 4 warps per SM (more CTAs only help overlap the
+// load/store phases), with full-width warps preferred when shared memory allows.
 void pick_geometry(int K, size_t smem_per_sm, size_t smem_per_block, int *NC, int *NCP, size_t *bytes) {
-    long best_cols = -1;
+    long best_score = -1;
+    *NC = 0;
     for (int nc = 32; nc >= 8; --nc) {
         const int ncp = nc | 1;
         const size_t b = (size_t)2 * K * ncp * sizeof(double);
         if (b > smem_per_block) continue;
         long ctas = (long)(smem_per_sm / (b + 1024));
-        if (ctas > 32) ctas = 32;
-        const long cols = ctas * nc;
-        if (cols > best_cols) { best_cols = cols; *NC = nc; *NCP = ncp; *bytes = b; }
+        if (ctas > 8) ctas = 8;
+        const long score = (ctas < 4 ? ctas : 4) * nc * 16 + ctas;   // columns on <=4 warps, then more CTAs
+        if (score > best_score) { best_score = score; *NC = nc; *NCP = ncp; *bytes = b; }
     }
-    if (best_cols < 0) { *NC = 0; }
 }
 
 }  // namespace
