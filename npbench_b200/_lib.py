@@ -42,6 +42,7 @@ PROTOTYPES = {
     "npb_jacobi2d_block_f64": (_int, [_int, _i64, _i64, _vp, _vp, _i64, _i64]),
     "npb_jacobi2d_tile_rows": (_int, []),
     "npb_heat3d_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp]),
+    "npb_heat3d_set_mode": (_int, [_int]),
     "npb_heat3d_sweep_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _i64, _i64]),
     "npb_fdtd2d_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "npb_fdtd2d_step_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64]),

@@ -47,6 +47,215 @@ heat3d_sweep_kernel(int n1, int n2, long long plane, const double *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Resident variant for grids that fit on chip (NPBench presets S/M/L).
+//
+// One cooperative launch runs ALL sweeps.  The interior (i,j) plane is cut into
+// PI x PJ tiles, one CTA (= one SM) each; a CTA keeps its tile (all k) plus a
+// one-cell halo ring in shared memory, double buffered (even / odd states), for
+// the whole time loop.  Per sweep a CTA
+//   1. waits until its <= 4 edge neighbours have published the previous state
+//      (one progress counter per CTA in global memory, acquire/release), and
+//      pulls their boundary rows from L2 into its halo ring;
+//   2. updates its own boundary rows first, storing them to shared memory AND
+//      to the global array of that state's parity (A even, B odd), which doubles
+//      as the mailbox the neighbours read; then publishes its progress counter;
+//   3. updates the remaining rows while the published rows travel.
+// No grid-wide barrier, no kernel boundary per sweep: a sweep costs one L2
+// round trip instead of a launch.  The last two sweeps write every cell, so on
+// return B holds state S-1 and A state S exactly like the reference.
+// The 7-point stencil needs no corner halos.  Same arithmetic as the sweep
+// kernel (NumPy order, -fmad=false).
+// ---------------------------------------------------------------------------
+constexpr int HR_THREADS = 512;
+
+struct ResidentParams {
+    int n0, n1, n2;          // grid extents
+    int PI, PJ;              // tiles along i and j
+    int ti_max, tj_max;      // largest tile extents (shared-memory strides)
+    int nsweeps;
+    double *A, *B;
+    unsigned *progress;      // [PI*PJ], zeroed before launch
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void tile_bounds(int n_int, int parts, int t, int &lo, int &hi) {
+    const int base = n_int / parts, rem = n_int % parts;      // interior index 0 == global index 1
+    lo = 1 + t * base + min(t, rem);
+    hi = lo + base + (t < rem ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(HR_THREADS, 1)
+heat3d_resident_kernel(ResidentParams p) {
+    extern __shared__ double sm[];
+    __shared__ unsigned short rowlist[1024];     // (ii << 8 | jj), boundary rows first
+    __shared__ int n_boundary_rows;
+
+    const int tid = threadIdx.x;
+    const int ti = blockIdx.x / p.PJ, tj = blockIdx.x % p.PJ;
+    int ilo, ihi, jlo, jhi;
+    tile_bounds(p.n0 - 2, p.PI, ti, ilo, ihi);
+    tile_bounds(p.n1 - 2, p.PJ, tj, jlo, jhi);
+    const int nit = ihi - ilo, njt = jhi - jlo;
+    const int n2 = p.n2, nk = n2 - 2;
+    const int rs = n2;                                   // shared row stride (doubles)
+    const int ps = (p.tj_max + 2) * rs;                  // shared plane stride
+    const size_t bufsz = (size_t)(p.ti_max + 2) * ps;
+    double *buf[2] = {sm, sm + bufsz};
+    double *X[2] = {p.A, p.B};
+    const long long grs = n2, gps = (long long)p.n1 * n2; // global row / plane stride
+
+    // neighbours: 0 = i-1, 1 = i+1, 2 = j-1, 3 = j+1
+    const bool has_nb[4] = {ti > 0, ti < p.PI - 1, tj > 0, tj < p.PJ - 1};
+    const int nb_id[4] = {(ti - 1) * p.PJ + tj, (ti + 1) * p.PJ + tj, ti * p.PJ + tj - 1, ti * p.PJ + tj + 1};
+
+    if (tid == 0) {
+        int n = 0;
+        for (int ii = 0; ii < nit; ++ii)
+            for (int jj = 0; jj < njt; ++jj)
+                if (ii == 0 || ii == nit - 1 || jj == 0 || jj == njt - 1) rowlist[n++] = (unsigned short)((ii << 8) | jj);
+        n_boundary_rows = n;
+        for (int ii = 1; ii < nit - 1; ++ii)
+            for (int jj = 1; jj < njt - 1; ++jj) rowlist[n++] = (unsigned short)((ii << 8) | jj);
+    }
+
+    // initial state: tile + halo ring of A -> buf[0] (state 0); same region of B -> buf[1]
+    // (B contributes the constant borders every odd state carries).
+    {
+        const int rows = (nit + 2) * (njt + 2);
+        for (int w = tid; w < rows * n2; w += HR_THREADS) {
+            const int r = w / n2, k = w - r * n2;
+            const int ii = r / (njt + 2), jj = r - ii * (njt + 2);      // ring coordinates
+            const long long g = (long long)(ilo - 1 + ii) * gps + (long long)(jlo - 1 + jj) * grs + k;
+            const int l = ii * ps + jj * rs + k;
+            buf[0][l] = __ldg(p.A + g);
+            buf[1][l] = __ldg(p.B + g);
+        }
+    }
+    __syncthreads();
+    const int nrows_all = nit * njt;
+    const int nrows_b = n_boundary_rows;
+
+    for (int s = 1; s <= p.nsweeps; ++s) {
+        const double *cur = buf[(s - 1) & 1];
+        double *nxt = buf[s & 1];
+        double *gout = X[s & 1];
+        if (s > 1) {
+            // ---- 1. wait for the neighbours' state s-1, pull their boundary rows
+            if (tid < 4 && has_nb[tid]) {
+                const unsigned *f = p.progress + nb_id[tid];
+                while (ld_acquire_u32(f) < (unsigned)(s - 1)) { }
+            }
+            __syncthreads();
+            const double *gin = X[(s - 1) & 1];
+            double *curw = buf[(s - 1) & 1];
+            // halo rows: (ilo-1, j) and (ihi, j) for j in tile; (i, jlo-1) and (i, jhi) for i in tile
+            const int nhalo_rows = 2 * njt + 2 * nit;
+            for (int w = tid; w < nhalo_rows * n2; w += HR_THREADS) {
+                const int r = w / n2, k = w - r * n2;
+                int ii, jj, side;
+                if (r < njt) { ii = 0; jj = r + 1; side = 0; }
+                else if (r < 2 * njt) { ii = nit + 1; jj = r - njt + 1; side = 1; }
+                else if (r < 2 * njt + nit) { ii = r - 2 * njt + 1; jj = 0; side = 2; }
+                else { ii = r - 2 * njt - nit + 1; jj = njt + 1; side = 3; }
+                if (has_nb[side]) {
+                    const long long g = (long long)(ilo - 1 + ii) * gps + (long long)(jlo - 1 + jj) * grs + k;
+                    curw[ii * ps + jj * rs + k] = __ldcg(gin + g);      // L2, never a stale L1 line
+                }
+            }
+            __syncthreads();
+        }
+        const bool write_all = (s >= p.nsweeps - 1);
+        // ---- 2 + 3. boundary rows (stored to the mailbox array too), publish, then the rest
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int r_begin = pass == 0 ? 0 : nrows_b;
+            const int r_end = pass == 0 ? nrows_b : nrows_all;
+            const bool to_global = (pass == 0) || write_all;
+            const int items = (r_end - r_begin) * nk;
+            for (int w = tid; w < items; w += HR_THREADS) {
+                const int r = w / nk, k = 1 + (w - r * nk);
+                const unsigned rc = rowlist[r_begin + r];
+                const int ii = (int)(rc >> 8), jj = (int)(rc & 255);
+                const double *c = cur + (ii + 1) * ps + (jj + 1) * rs + k;
+                const double ce = c[0];
+                const double c2 = 2.0 * ce;
+                const double t1 = 0.125 * ((c[ps] - c2) + c[-ps]);
+                const double t2 = 0.125 * ((c[rs] - c2) + c[-rs]);
+                const double t3 = 0.125 * ((c[1] - c2) + c[-1]);
+                const double v = ((t1 + t2) + t3) + ce;
+                nxt[(ii + 1) * ps + (jj + 1) * rs + k] = v;
+                if (to_global) gout[(long long)(ilo + ii) * gps + (long long)(jlo + jj) * grs + k] = v;
+            }
+            if (pass == 0) {
+                __syncthreads();                         // every boundary-row store of this CTA is issued
+                if (tid == 0) {
+                    __threadfence();
+                    st_release_u32(p.progress + blockIdx.x, (unsigned)s);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Returns 1 if the resident kernel ran, 0 if the problem is not eligible, <0 on error.
+int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B) {
+    if (nsweeps < 4 || n0 > 4096 || n1 > 4096 || n2 > 4096) return 0;
+    const int sms = npb::st().sm_count;
+    const int in0 = (int)n0 - 2, in1 = (int)n1 - 2;
+    // tiles: as square as possible, PI*PJ <= #SMs, each extent at most the interior size
+    int PI = 1, PJ = 1;
+    {
+        long best = -1;
+        for (int a = 1; a <= in0 && a <= sms; ++a) {
+            int b = sms / a;
+            if (b > in1) b = in1;
+            if (b < 1) continue;
+            const int ta = (in0 + a - 1) / a, tb = (in1 + b - 1) / b;
+            // minimise the largest tile (work per sweep), then its perimeter
+            const long cost = (long)ta * tb * 1000 + (ta + tb);
+            if (best < 0 || cost < best) { best = cost; PI = a; PJ = b; }
+        }
+    }
+    const int ti_max = (in0 + PI - 1) / PI, tj_max = (in1 + PJ - 1) / PJ;
+    if (ti_max > 255 || tj_max > 255 || ti_max * tj_max > 1024) return 0;
+    const size_t smem = (size_t)2 * (ti_max + 2) * (tj_max + 2) * n2 * sizeof(double);
+    if (smem > npb::st().smem_optin) return 0;
+    static size_t configured = 0;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(heat3d_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)npb::st().smem_optin) != cudaSuccess) { cudaGetLastError(); return 0; }
+        configured = npb::st().smem_optin;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, heat3d_resident_kernel, HR_THREADS, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if ((long)per_sm * sms < (long)PI * PJ) return 0;      // all CTAs must be co-resident
+    unsigned *progress = (unsigned *)npb::workspace(1, 4096 * sizeof(unsigned));
+    if (!progress) return 0;
+    if (cudaMemsetAsync(progress, 0, (size_t)PI * PJ * sizeof(unsigned), npb::st().stream) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    ResidentParams rp{(int)n0, (int)n1, (int)n2, PI, PJ, ti_max, tj_max, (int)nsweeps, A, B, progress};
+    void *args[] = {&rp};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)heat3d_resident_kernel, dim3(PI * PJ), dim3(HR_THREADS),
+                                                args, smem, npb::st().stream);
+    if (e != cudaSuccess) return -npb::fail_cuda("heat3d_resident_kernel", e);
+    npb::count_launch();
+    return 1;
+}
+
 int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst, int64_t i_lo,
                  int64_t i_hi) {
     if (i_lo < 1) i_lo = 1;
@@ -67,7 +276,12 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     return 0;
 }
 
+bool g_force_streaming = false;
+
 }  // namespace
+
+// 0: size-based dispatch (default); 1: always one launch per sweep (streaming kernel)
+extern "C" int npb_heat3d_set_mode(int mode) { g_force_streaming = (mode == 1); return 0; }
 
 extern "C" int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src,
                                     double *dst, int64_t i_lo, int64_t i_hi) {
@@ -86,6 +300,11 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
     NPB_ARG(n1 < (1LL << 31) && n2 < (1LL << 31) && n1 * n2 < (1LL << 40), "npb_heat3d_f64",
             "plane too large");
     if (tsteps <= 1 || n0 < 3 || n1 < 3 || n2 < 3) return 0;
+    if (!g_force_streaming) {
+        const int r = try_resident(2 * (tsteps - 1), n0, n1, n2, A, B);
+        if (r < 0) return -r;
+        if (r == 1) return 0;
+    }
     for (int64_t t = 1; t < tsteps; ++t) {   // heat_3d_numpy.py:6
         int rc = launch_sweep(n0, n1, n2, A, B, 1, n0 - 1);
         if (rc) return rc;

@@ -6,7 +6,7 @@
 //
 // Layout problem: arrays are (I,J,K) with K -- the recurrence axis --
 // contiguous, so "one column per thread" has a lane stride of K*8 bytes.
-// Design: one single-warp CTA owns NC consecutive columns (one contiguous
+// Design: one small CTA (4 warps) owns NC <= 32 consecutive columns (one contiguous
 // NC*K*8-byte chunk per array) and runs four phases over a shared-memory tile
 // [K][NCP] (NCP odd => conflict-free both for lanes-along-k and
 // lanes-along-column accesses):
@@ -20,9 +20,10 @@
 //   D  lanes along k: utens_stage = dtr*(datacol - u_pos), coalesced store.
 // All HBM traffic is coalesced; ccol/dcol never leave the SM (the reference
 // allocates them as full (I,J,K) temporaries, vadv_numpy.py:11-12).
-// Several single-warp CTAs per SM are resident (as many as shared memory
-// allows), so phase A/D traffic of one overlaps the latency-bound B/C of
-// the others.  No __syncthreads: one warp per CTA, __syncwarp between phases.
+// All warps of the CTA take part in the coalesced phases A and D (memory-level
+// parallelism), the first NC threads run the serial phases B and C.  Several
+// CTAs per SM are resident (as many as shared memory allows), so phase A/D
+// traffic of one overlaps the latency-bound B/C of the others.
 //
 // Identities used (exact in binary64): BET_M == BET_P == 0.5, hence
 // as == acol and cs == ccol-before-division; and gcv_k*0.5 == -(gav_{k+1}*0.5)
@@ -32,6 +33,8 @@
 
 namespace {
 
+constexpr int VA_WARPS = 4;                 // warps per CTA: all of them load/store (phases A, D),
+constexpr int VA_THREADS = 32 * VA_WARPS;   // the first NC threads run the per-column solve (B, C)
 constexpr int VA_U = 6;    // phase-A work items loaded per batch
 constexpr int VD_U = 10;   // phase-D work items loaded per batch
 
@@ -46,13 +49,14 @@ struct VadvParams {
     const double *u_stage, *wcon, *u_pos, *utens;
 };
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(VA_THREADS, 4)
 vadv_warp_kernel(VadvParams p) {
     extern __shared__ double tile[];
     const int K = p.K, NCP = p.NCP;
     double *tA = tile;                     // a_k   -> ccol_k
     double *tD = tile + (size_t)K * NCP;   // dc_k  -> dcol_k -> datacol_k
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const long long col0 = (long long)blockIdx.x * p.NC;
     const int nc = (int)min((long long)p.NC, p.ncols - col0);
     const double dtr = p.dtr;
@@ -65,7 +69,7 @@ vadv_warp_kernel(VadvParams p) {
     // levels use clamped indices and selects instead of branches.
     const int nkb = (K + 31) >> 5;
     const int items = nc * nkb;
-    for (int it0 = 0; it0 < items; it0 += VA_U) {
+    for (int it0 = warp * VA_U; it0 < items; it0 += VA_WARPS * VA_U) {
         double r_um[VA_U], r_uc[VA_U], r_un[VA_U], r_wc[VA_U], r_wn[VA_U], r_d0a[VA_U], r_ut[VA_U], r_uo[VA_U];
         int r_k[VA_U], r_cc[VA_U];
 #pragma unroll
@@ -105,12 +109,12 @@ vadv_warp_kernel(VadvParams p) {
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---------------- phase B + C: lanes along columns --------------------
-    if (lane < nc) {
-        double *cA = tA + lane;
-        double *cD = tD + lane;
+    if (threadIdx.x < nc) {
+        double *cA = tA + threadIdx.x;
+        double *cD = tD + threadIdx.x;
         // k = 0 : vadv_numpy.py:19-30   ccol = gcv*BET_P == -a_1
         double a_cur = cA[NCP];                              // a_1
         double a_nxt = cA[min(2, K - 1) * NCP];              // a_2
@@ -155,10 +159,10 @@ vadv_warp_kernel(VadvParams p) {
             c_k = c_pf; d_k = d_pf;
         }
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---------------- phase D: lanes along k ------------------------------
-    for (int it0 = 0; it0 < items; it0 += VD_U) {
+    for (int it0 = warp * VD_U; it0 < items; it0 += VA_WARPS * VD_U) {
         double r_up[VD_U];
 #pragma unroll
         for (int u = 0; u < VD_U; ++u) {
@@ -178,7 +182,7 @@ vadv_warp_kernel(VadvParams p) {
     }
 }
 
-// Pick NC (columns per single-warp CTA).  The forward sweep is a serial divide chain per
+// Pick NC (columns per CTA).  The forward sweep is a serial divide chain per
 // column; one warp per SM sub-partition already keeps the FP64 pipe ~85% busy, so the goal
 // is to maximise columns resident on up to 4 warps per SM (more CTAs only help overlap the
 // load/store phases), with full-width warps preferred when shared memory allows.
@@ -222,7 +226,7 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     p.utens_stage = utens_stage; p.u_stage = u_stage; p.wcon = wcon; p.u_pos = u_pos; p.utens = utens;
     const long long nblk = (p.ncols + NC - 1) / NC;
     NPB_ARG(nblk < (1LL << 31), "npb_vadv_f64", "too many columns");
-    vadv_warp_kernel<<<(unsigned)nblk, 32, bytes, npb::st().stream>>>(p);
+    vadv_warp_kernel<<<(unsigned)nblk, VA_THREADS, bytes, npb::st().stream>>>(p);
     NPB_CHECK_LAUNCH("vadv_warp_kernel");
     npb::count_launch();
     return 0;
