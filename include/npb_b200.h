@@ -89,6 +89,7 @@ int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A
 /* 0 = dispatch by size (on-chip resident persistent kernel when the grid fits, else one
  * streaming launch per sweep); 1 = always the streaming kernel (tests, profiling) */
 int npb_heat3d_set_mode(int mode);
+int npb_heat3d_last_path(void);          /* variant used by the last call: 1 resident, 2 streaming */
 /* one sweep src -> dst over planes [i_lo, i_hi) (clamped to the interior) */
 int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
                          int64_t i_lo, int64_t i_hi);
@@ -111,6 +112,9 @@ int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t 
  * in (I+4, J+4, K); out, coeff (I, J, K). */
 int npb_hdiff_f64(int64_t I, int64_t J, int64_t K, const double *in_field, double *out_field,
                   const double *coeff);
+/* 0 = dispatch by size; 1 = register-marching kernel; 2 = TMA-bulk ring kernel when legal */
+int npb_hdiff_set_mode(int mode);
+int npb_hdiff_last_path(void);           /* 1 marching, 2 ring */
 
 /* vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage):
  * weather_stencils/vadv/vadv_numpy.py:9-78.  All (I,J,K) but wcon (I+1,J,K). K >= 2. */
