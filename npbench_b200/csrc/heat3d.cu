@@ -257,6 +257,165 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
     return 1;
 }
 
+// ---------------------------------------------------------------------------
+// Temporally blocked variant for small (L2-resident) grids: NPBench S / M / L.
+//
+// At 70^3 a sweep is ~2 us of latency and a launch costs ~4 us, so the time loop
+// is bound by the NUMBER of launches.  One launch of this kernel advances the
+// grid by `nsteps` (1 or 3) sweeps: a CTA loads a TI x TJ tile of (i,j) columns
+// (all k) plus an nsteps-deep halo ring into shared memory, runs the sweeps on a
+// shrinking region between two shared buffers, and writes the tile centre.  As
+// in jacobi2d.cu nsteps is odd, so a pass always goes A -> B or B -> A and the
+// constant borders of each state's parity come from the right array.  Inside a
+// sweep a thread owns one (j,k) column of the region and marches along i with a
+// three-plane register window: 5 shared loads + 1 store per cell update.
+// ---------------------------------------------------------------------------
+constexpr int TB_H = 3;              // halo depth = max sweeps per launch
+constexpr int TB_THREADS = 512;
+
+struct TbParams {
+    int n0, n1, n2;
+    int T;                // tile edge (TI == TJ == T)
+    int tiles_j;
+    int nsteps;
+    const double *src;
+    double *dst;
+};
+
+__global__ void __launch_bounds__(TB_THREADS)
+heat3d_tb_kernel(TbParams p) {
+    extern __shared__ double sm[];
+    const int n2 = p.n2, nk = n2 - 2;
+    const int R = p.T + 2 * TB_H;                 // region edge (rows == cols)
+    const int ps = R * n2;                        // shared stride between i-planes of the region
+    double *buf0 = sm, *buf1 = sm + (size_t)R * ps;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ti = blockIdx.x / p.tiles_j, tj = blockIdx.x % p.tiles_j;
+    const int i0 = 1 + ti * p.T, j0 = 1 + tj * p.T;       // first output (i, j)
+    const int gi_base = i0 - TB_H, gj_base = j0 - TB_H;    // region (r, c) <-> global (gi_base + r, gj_base + c)
+    const int h = p.nsteps;
+    const long long grs = n2, gps = (long long)p.n1 * n2;
+
+    // ---- load rows (r, c) of the region that lie within h of the tile, clipped to the grid
+    const int li_lo = max(0, i0 - h), li_hi = min(p.n0 - 1, i0 + p.T - 1 + h);
+    const int lj_lo = max(0, j0 - h), lj_hi = min(p.n1 - 1, j0 + p.T - 1 + h);
+    for (int row = warp; row < R * R; row += TB_THREADS / 32) {
+        const int r = row / R, c = row - r * R;
+        const int gi = gi_base + r, gj = gj_base + c;
+        if (gi < li_lo || gi > li_hi || gj < lj_lo || gj > lj_hi) continue;
+        const double *gs = p.src + gi * gps + gj * grs;
+        const double *gd = p.dst + gi * gps + gj * grs;
+        double *s0 = buf0 + r * ps + c * n2, *s1 = buf1 + r * ps + c * n2;
+        const bool border = (gi == 0 || gi == p.n0 - 1 || gj == 0 || gj == p.n1 - 1);
+        for (int k = lane; k < n2; k += 32) {
+            s0[k] = __ldg(gs + k);
+            // states of dst's parity: constant border rows and the two constant k-border cells
+            if (border || k == 0 || k == n2 - 1) s1[k] = __ldg(gd + k);
+        }
+    }
+    __syncthreads();
+
+    // ---- nsteps sweeps on a shrinking region
+    for (int s = 1; s <= p.nsteps; ++s) {
+        const double *in = (s & 1) ? buf0 : buf1;
+        double *out = (s & 1) ? buf1 : buf0;
+        const int ui_lo = max(1, i0 - h + s), ui_hi = min(p.n0 - 2, i0 + p.T - 1 + h - s);
+        const int uj_lo = max(1, j0 - h + s), uj_hi = min(p.n1 - 2, j0 + p.T - 1 + h - s);
+        const int r_lo = ui_lo - gi_base, r_hi = ui_hi - gi_base;
+        const int c_lo = uj_lo - gj_base, ncols = (uj_hi - uj_lo + 1) * nk;
+        if (r_hi >= r_lo) {
+            for (int col = tid; col < ncols; col += TB_THREADS) {
+                const int cj = col / nk;
+                const int k = 1 + (col - cj * nk);
+                const double *q = in + r_lo * ps + (c_lo + cj) * n2 + k;
+                double *o = out + r_lo * ps + (c_lo + cj) * n2 + k;
+                double up = q[-ps], ce = q[0];
+                for (int r = r_lo; r <= r_hi; ++r) {
+                    const double dn = q[ps];
+                    const double jm = q[-n2], jp = q[n2];
+                    const double km = q[-1], kp = q[1];
+                    const double c2 = 2.0 * ce;
+                    const double t1 = 0.125 * ((dn - c2) + up);
+                    const double t2 = 0.125 * ((jp - c2) + jm);
+                    const double t3 = 0.125 * ((kp - c2) + km);
+                    *o = ((t1 + t2) + t3) + ce;
+                    up = ce; ce = dn;
+                    q += ps; o += ps;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- store the tile centre (interior cells) from the last buffer
+    const double *fin = (p.nsteps & 1) ? buf1 : buf0;
+    const int o_ihi = min(p.n0 - 2, i0 + p.T - 1), o_jhi = min(p.n1 - 2, j0 + p.T - 1);
+    for (int row = warp; row < p.T * p.T; row += TB_THREADS / 32) {
+        const int a = row / p.T, b = row - a * p.T;
+        const int gi = i0 + a, gj = j0 + b;
+        if (gi > o_ihi || gj > o_jhi) continue;
+        const double *f = fin + (a + TB_H) * ps + (b + TB_H) * n2;
+        double *g = p.dst + gi * gps + gj * grs;
+        for (int k = 1 + lane; k <= nk; k += 32) g[k] = f[k];
+    }
+}
+
+// Tile edge for the temporally blocked kernel, 0 if it should not be used.
+int tb_pick_tile(int64_t n0, int64_t n1, int64_t n2, size_t *smem_out) {
+    if (n0 * n1 * n2 > 600000 || n2 > 4096) return 0;       // large grids stream (one launch per sweep)
+    const int sms = npb::st().sm_count;
+    int best = 0;
+    double best_cost = 0.0;
+    for (int T = 8; T >= 2; --T) {
+        const size_t smem = (size_t)2 * (T + 2 * TB_H) * (T + 2 * TB_H) * n2 * sizeof(double);
+        if (smem + 2048 > npb::st().smem_optin) continue;
+        long per_sm = (long)((npb::st().smem_optin + 1024) / (smem + 1024));
+        if (per_sm > 2048 / TB_THREADS) per_sm = 2048 / TB_THREADS;
+        const long tiles = (long)((n0 - 2 + T - 1) / T) * (long)((n1 - 2 + T - 1) / T);
+        const long waves = (tiles + per_sm * sms - 1) / (per_sm * sms);
+        double work = 0.0;
+        for (int s = 1; s <= TB_H; ++s) work += (double)(T + 2 * TB_H - 2 * s) * (T + 2 * TB_H - 2 * s);
+        const double cost = (double)waves * (work + 40.0);   // +40: fixed latency per launch wave
+        if (best == 0 || cost < best_cost) { best = T; best_cost = cost; *smem_out = smem; }
+    }
+    return best;
+}
+
+int launch_tb(int T, size_t smem, int nsteps, int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        NPB_CUDA(cudaFuncSetAttribute(heat3d_tb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int tiles_i = (int)((n0 - 2 + T - 1) / T), tiles_j = (int)((n1 - 2 + T - 1) / T);
+    TbParams p{(int)n0, (int)n1, (int)n2, T, tiles_j, nsteps, src, dst};
+    heat3d_tb_kernel<<<tiles_i * tiles_j, TB_THREADS, smem, npb::st().stream>>>(p);
+    NPB_CHECK_LAUNCH("heat3d_tb_kernel");
+    npb::count_launch();
+    return 0;
+}
+
+// 2*(TSTEPS-1) sweeps as blocked passes (see jacobi2d.cu for the parity argument):
+// an odd number of odd-sized passes A->B, B->A, ..., A->B, then one single sweep B->A.
+int run_tb(int T, size_t smem, int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B) {
+    const int64_t M = nsweeps - 1;
+    int64_t n = (M + TB_H - 1) / TB_H;
+    if ((n & 1) == 0) ++n;
+    int64_t extra_pairs = (M - n) / 2;
+    const int64_t cap = (TB_H - 1) / 2;
+    double *src = A, *dst = B;
+    for (int64_t q = 0; q < n; ++q) {
+        const int64_t left = n - q;
+        int64_t take = (extra_pairs + left - 1) / left;
+        if (take > cap) take = cap;
+        extra_pairs -= take;
+        const int rc = launch_tb(T, smem, (int)(1 + 2 * take), n0, n1, n2, src, dst);
+        if (rc) return rc;
+        double *t = src; src = dst; dst = t;
+    }
+    return launch_tb(T, smem, 1, n0, n1, n2, src, dst);
+}
+
 int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst, int64_t i_lo,
                  int64_t i_hi) {
     if (i_lo < 1) i_lo = 1;
@@ -277,14 +436,15 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     return 0;
 }
 
-bool g_force_streaming = false;
-int g_last_path = 0;   // 1 = resident persistent kernel, 2 = one launch per sweep
+int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 prefer the resident persistent kernel
+int g_last_path = 0;   // 1 resident persistent kernel, 2 one launch per sweep, 3 temporally blocked passes
 
 }  // namespace
 
-// 0: size-based dispatch (default); 1: always one launch per sweep (streaming kernel)
-extern "C" int npb_heat3d_set_mode(int mode) { g_force_streaming = (mode == 1); return 0; }
-// which variant the last npb_heat3d_f64 call used: 1 = resident, 2 = streaming, 0 = none yet
+// 0: size-based dispatch (default: temporally blocked passes for small grids, else streaming);
+// 1: always one launch per sweep; 2: prefer the on-chip resident persistent kernel
+extern "C" int npb_heat3d_set_mode(int mode) { g_mode = mode; return 0; }
+// variant used by the last npb_heat3d_f64 call: 1 resident, 2 streaming, 3 temporally blocked
 extern "C" int npb_heat3d_last_path(void) { return g_last_path; }
 
 extern "C" int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src,
@@ -304,10 +464,15 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
     NPB_ARG(n1 < (1LL << 31) && n2 < (1LL << 31) && n1 * n2 < (1LL << 40), "npb_heat3d_f64",
             "plane too large");
     if (tsteps <= 1 || n0 < 3 || n1 < 3 || n2 < 3) return 0;
-    if (!g_force_streaming) {
+    if (g_mode == 2) {                       // on-chip resident persistent kernel (opt-in)
         const int r = try_resident(2 * (tsteps - 1), n0, n1, n2, A, B);
         if (r < 0) return -r;
         if (r == 1) { g_last_path = 1; return 0; }
+    }
+    if (g_mode != 1) {                       // default: temporally blocked passes for small grids
+        size_t smem = 0;
+        const int T = tb_pick_tile(n0, n1, n2, &smem);
+        if (T > 0) { g_last_path = 3; return run_tb(T, smem, 2 * (tsteps - 1), n0, n1, n2, A, B); }
     }
     g_last_path = 2;
     for (int64_t t = 1; t < tsteps; ++t) {   // heat_3d_numpy.py:6
