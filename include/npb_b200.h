@@ -86,9 +86,10 @@ int npb_jacobi2d_tile_rows(void);        /* rows per tile of the blocked kernel 
 
 /* kernel(TSTEPS, A, B): polybench/heat_3d/heat_3d_numpy.py:4-20.  (n0,n1,n2). */
 int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B);
-/* 0 = dispatch by size (temporally blocked shared-memory passes for L2-resident grids, else
- * one streaming launch per sweep); 1 = always streaming; 2 = prefer the on-chip resident
- * persistent kernel (neighbour-flag halo exchange) when the grid fits */
+/* 0 = dispatch by size (on-chip resident persistent kernel with in-L2 halo inboxes when the
+ * grid fits in shared memory, else one streaming launch per sweep); 1 = always streaming;
+ * 3 = temporally blocked shared-memory passes (3 sweeps per launch; measured slower, kept
+ * for comparison) */
 int npb_heat3d_set_mode(int mode);
 int npb_heat3d_last_path(void);          /* last call: 1 resident, 2 streaming, 3 blocked */
 /* one sweep src -> dst over planes [i_lo, i_hi) (clamped to the interior) */

@@ -13,6 +13,8 @@
 // Arithmetic (NumPy order, one rounding per op; -fmad=false):
 //   ((0.125*((A[i+1]-2c)+A[i-1]) + 0.125*((A[j+1]-2c)+A[j-1]))
 //     + 0.125*((A[k+1]-2c)+A[k-1])) + c
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -53,38 +55,48 @@ heat3d_sweep_kernel(int n1, int n2, long long plane, const double *__restrict__ 
 // One cooperative launch runs ALL sweeps.  The interior (i,j) plane is cut into
 // PI x PJ tiles, one CTA (= one SM) each; a CTA keeps its tile (all k) plus a
 // one-cell halo ring in shared memory, double buffered (even / odd states), for
-// the whole time loop.  Per sweep a CTA
-//   1. waits until its <= 4 edge neighbours have published the previous state
-//      (one progress counter per CTA in global memory, acquire/release), and
-//      pulls their boundary rows from L2 into its halo ring;
-//   2. updates its own boundary rows first, storing them to shared memory AND
-//      to the global array of that state's parity (A even, B odd), which doubles
-//      as the mailbox the neighbours read; then publishes its progress counter;
-//   3. updates the remaining rows while the published rows travel.
-// No grid-wide barrier, no kernel boundary per sweep: a sweep costs one L2
-// round trip instead of a launch.  The last two sweeps write every cell, so on
-// return B holds state S-1 and A state S exactly like the reference.
-// The 7-point stencil needs no corner halos.  Same arithmetic as the sweep
-// kernel (NumPy order, -fmad=false).
+// the whole time loop.  Halos travel through per-CTA inboxes in global memory
+// (L2) WITHOUT flags or fences on the critical path: every inbox cell starts as
+// a signalling-NaN bit pattern that floating-point arithmetic can never produce
+// (results are always quiet NaNs), the sender stores the freshly computed face
+// value straight from its update loop (st.relaxed.gpu), and the receiver spins on the
+// cell itself (ld.relaxed.gpu) until the sentinel is gone, copies the value into its
+// shared halo ring and re-arms the cell.  Inboxes are a ring of HR_SLOTS sweeps, so
+// a cell is rewritten HR_SLOTS sweeps after it was re-armed; a gpu-scope fence every
+// few sweeps (off the critical path) orders the re-arm before that rewrite.  A sweep therefore
+// costs one store->L2->load round trip plus one __syncthreads, not a launch.
+// The last two sweeps write every cell to B / A, so on return B holds state S-1
+// and A state S exactly like the reference.  The 7-point stencil needs no corner
+// halos.  Same arithmetic as the sweep kernel (NumPy order, -fmad=false).
 // ---------------------------------------------------------------------------
 constexpr int HR_THREADS = 512;
+constexpr int HR_SLOTS = 12;         // inbox ring depth (sweeps)
+constexpr int HR_FENCE_EVERY = 4;    // gpu-scope fence cadence (sweeps); needs 2*cadence <= HR_SLOTS
+constexpr int HR_RECV = 4;           // inbox cells requested per thread before the first test
+constexpr unsigned long long HR_SENTINEL = 0x7FF400017FF40001ULL;   // sNaN: never an arithmetic result
 
 struct ResidentParams {
     int n0, n1, n2;          // grid extents
     int PI, PJ;              // tiles along i and j
     int ti_max, tj_max;      // largest tile extents (shared-memory strides)
+    int face_rows;           // rows per inbox side (max(ti_max, tj_max))
     int nsweeps;
     double *A, *B;
-    unsigned *progress;      // [PI*PJ], zeroed before launch
+    unsigned long long *inbox;   // [PI*PJ][HR_SLOTS][4 sides][face_rows][n2-2]
+    int fences;                  // 1: periodic gpu-scope fences (formal release/acquire chain)
+    unsigned backoff_ns;
 };
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void tile_bounds(int n_int, int parts, int t, int &lo, int &hi) {
     const int base = n_int / parts, rem = n_int % parts;      // interior index 0 == global index 1
@@ -95,9 +107,6 @@ __device__ __forceinline__ void tile_bounds(int n_int, int parts, int t, int &lo
 __global__ void __launch_bounds__(HR_THREADS, 1)
 heat3d_resident_kernel(ResidentParams p) {
     extern __shared__ double sm[];
-    __shared__ unsigned short rowlist[1024];     // (ii << 8 | jj), boundary rows first
-    __shared__ int n_boundary_rows;
-
     const int tid = threadIdx.x;
     const int ti = blockIdx.x / p.PJ, tj = blockIdx.x % p.PJ;
     int ilo, ihi, jlo, jhi;
@@ -108,26 +117,18 @@ heat3d_resident_kernel(ResidentParams p) {
     const int rs = n2;                                   // shared row stride (doubles)
     const int ps = (p.tj_max + 2) * rs;                  // shared plane stride
     const size_t bufsz = (size_t)(p.ti_max + 2) * ps;
-    double *buf[2] = {sm, sm + bufsz};
-    double *X[2] = {p.A, p.B};
+    double *const buf0 = sm, *const buf1 = sm + bufsz;
     const long long grs = n2, gps = (long long)p.n1 * n2; // global row / plane stride
 
-    // neighbours: 0 = i-1, 1 = i+1, 2 = j-1, 3 = j+1
+    // neighbours: side 0 = i-1, 1 = i+1, 2 = j-1, 3 = j+1
     const bool has_nb[4] = {ti > 0, ti < p.PI - 1, tj > 0, tj < p.PJ - 1};
     const int nb_id[4] = {(ti - 1) * p.PJ + tj, (ti + 1) * p.PJ + tj, ti * p.PJ + tj - 1, ti * p.PJ + tj + 1};
+    const size_t side_sz = (size_t)p.face_rows * nk, slot_sz = 4 * side_sz, box_sz = HR_SLOTS * slot_sz;
+    unsigned long long *my_box = p.inbox + (size_t)blockIdx.x * box_sz;
 
-    if (tid == 0) {
-        int n = 0;
-        for (int ii = 0; ii < nit; ++ii)
-            for (int jj = 0; jj < njt; ++jj)
-                if (ii == 0 || ii == nit - 1 || jj == 0 || jj == njt - 1) rowlist[n++] = (unsigned short)((ii << 8) | jj);
-        n_boundary_rows = n;
-        for (int ii = 1; ii < nit - 1; ++ii)
-            for (int jj = 1; jj < njt - 1; ++jj) rowlist[n++] = (unsigned short)((ii << 8) | jj);
-    }
-
-    // initial state: tile + halo ring of A -> buf[0] (state 0); same region of B -> buf[1]
-    // (B contributes the constant borders every odd state carries).
+    // arm my inbox, load the initial state: tile + halo ring of A -> buf[0] (state 0), same region
+    // of B -> buf[1] (B contributes the constant borders every odd state carries)
+    for (size_t w = tid; w < box_sz; w += HR_THREADS) my_box[w] = HR_SENTINEL;
     {
         const int rows = (nit + 2) * (njt + 2);
         for (int w = tid; w < rows * n2; w += HR_THREADS) {
@@ -135,83 +136,123 @@ heat3d_resident_kernel(ResidentParams p) {
             const int ii = r / (njt + 2), jj = r - ii * (njt + 2);      // ring coordinates
             const long long g = (long long)(ilo - 1 + ii) * gps + (long long)(jlo - 1 + jj) * grs + k;
             const int l = ii * ps + jj * rs + k;
-            buf[0][l] = __ldg(p.A + g);
-            buf[1][l] = __ldg(p.B + g);
+            buf0[l] = __ldg(p.A + g);
+            buf1[l] = __ldg(p.B + g);
         }
     }
-    __syncthreads();
-    const int nrows_all = nit * njt;
-    const int nrows_b = n_boundary_rows;
+    __threadfence();
+    cooperative_groups::this_grid().sync();              // every inbox is armed before anyone sends
+
+    const int ncols = njt * nk;                          // (jj, k) columns of the tile
+    const int nhalo = (2 * njt + 2 * nit) * nk;          // halo cells per sweep (<= HR_THREADS * HR_RECV)
+
+    // receive descriptors of this thread (sweep invariant): inbox cell offset within a slot and
+    // destination in the shared halo ring
+    int roff[HR_RECV], rdst[HR_RECV];
+    unsigned rmask = 0;
+#pragma unroll
+    for (int u = 0; u < HR_RECV; ++u) {
+        const int w = u * HR_THREADS + tid;
+        roff[u] = 0; rdst[u] = 0;
+        if (w < nhalo) {
+            const int r = w / nk, kk = w - r * nk;
+            int side, row, ii, jj;
+            if (r < njt) { side = 0; row = r; ii = 0; jj = row + 1; }
+            else if (r < 2 * njt) { side = 1; row = r - njt; ii = nit + 1; jj = row + 1; }
+            else if (r < 2 * njt + nit) { side = 2; row = r - 2 * njt; ii = row + 1; jj = 0; }
+            else { side = 3; row = r - 2 * njt - nit; ii = row + 1; jj = njt + 1; }
+            if (has_nb[side]) {
+                roff[u] = (int)(side * side_sz + (size_t)row * nk + kk);
+                rdst[u] = ii * ps + jj * rs + 1 + kk;
+                rmask |= 1u << u;
+            }
+        }
+    }
 
     for (int s = 1; s <= p.nsweeps; ++s) {
-        const double *cur = buf[(s - 1) & 1];
-        double *nxt = buf[s & 1];
-        double *gout = X[s & 1];
+        double *cur = (s & 1) ? buf0 : buf1;          // state s-1
+        double *nxt = (s & 1) ? buf1 : buf0;          // state s
+        double *gout = (s & 1) ? p.B : p.A;
         if (s > 1) {
-            // ---- 1. wait for the neighbours' state s-1, pull their boundary rows
-            if (tid < 4 && has_nb[tid]) {
-                const unsigned *f = p.progress + nb_id[tid];
-                while (ld_acquire_u32(f) < (unsigned)(s - 1)) { }
-            }
-            __syncthreads();
-            const double *gin = X[(s - 1) & 1];
-            double *curw = buf[(s - 1) & 1];
-            // halo rows: (ilo-1, j) and (ihi, j) for j in tile; (i, jlo-1) and (i, jhi) for i in tile
-            const int nhalo_rows = 2 * njt + 2 * nit;
-            for (int w = tid; w < nhalo_rows * n2; w += HR_THREADS) {
-                const int r = w / n2, k = w - r * n2;
-                int ii, jj, side;
-                if (r < njt) { ii = 0; jj = r + 1; side = 0; }
-                else if (r < 2 * njt) { ii = nit + 1; jj = r - njt + 1; side = 1; }
-                else if (r < 2 * njt + nit) { ii = r - 2 * njt + 1; jj = 0; side = 2; }
-                else { ii = r - 2 * njt - nit + 1; jj = njt + 1; side = 3; }
-                if (has_nb[side]) {
-                    const long long g = (long long)(ilo - 1 + ii) * gps + (long long)(jlo - 1 + jj) * grs + k;
-                    curw[ii * ps + jj * rs + k] = __ldcg(gin + g);      // L2, never a stale L1 line
-                }
-            }
-            __syncthreads();
-        }
-        const bool write_all = (s >= p.nsweeps - 1);
-        // ---- 2 + 3. boundary rows (stored to the mailbox array too), publish, then the rest
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            const int r_begin = pass == 0 ? 0 : nrows_b;
-            const int r_end = pass == 0 ? nrows_b : nrows_all;
-            const bool to_global = (pass == 0) || write_all;
-            const int items = (r_end - r_begin) * nk;
-            for (int w = tid; w < items; w += HR_THREADS) {
-                const int r = w / nk, k = 1 + (w - r * nk);
-                const unsigned rc = rowlist[r_begin + r];
-                const int ii = (int)(rc >> 8), jj = (int)(rc & 255);
-                const double *c = cur + (ii + 1) * ps + (jj + 1) * rs + k;
-                const double ce = c[0];
-                const double c2 = 2.0 * ce;
-                const double t1 = 0.125 * ((c[ps] - c2) + c[-ps]);
-                const double t2 = 0.125 * ((c[rs] - c2) + c[-rs]);
-                const double t3 = 0.125 * ((c[1] - c2) + c[-1]);
-                const double v = ((t1 + t2) + t3) + ce;
-                nxt[(ii + 1) * ps + (jj + 1) * rs + k] = v;
-                if (to_global) gout[(long long)(ilo + ii) * gps + (long long)(jlo + jj) * grs + k] = v;
-            }
-            if (pass == 0) {
-                __syncthreads();                         // every boundary-row store of this CTA is issued
-                if (tid == 0) {
-                    __threadfence();
-                    st_release_u32(p.progress + blockIdx.x, (unsigned)s);
-                }
+            // ---- receive state s-1 faces: spin on each inbox cell until the sentinel is gone
+            unsigned long long *slot = my_box + (size_t)((s - 1) % HR_SLOTS) * slot_sz;
+            // All of a thread's cells are requested before any is tested, so the receive phase
+            // costs one L2 round trip (plus re-polls), not one per cell.
+            unsigned pending = rmask;
+            while (pending) {
+                unsigned long long v[HR_RECV];
+#pragma unroll
+                for (int u = 0; u < HR_RECV; ++u)
+                    if (pending & (1u << u)) v[u] = ld_relaxed_u64(slot + roff[u]);
+#pragma unroll
+                for (int u = 0; u < HR_RECV; ++u)
+                    if ((pending & (1u << u)) && v[u] != HR_SENTINEL) {
+                        cur[rdst[u]] = __longlong_as_double((long long)v[u]);
+                        st_relaxed_u64(slot + roff[u], HR_SENTINEL);       // re-arm for sweep s-1+HR_SLOTS
+                        pending &= ~(1u << u);
+                    }
+                if (pending) __nanosleep(p.backoff_ns);                    // keep re-polls off the L2's back
             }
         }
         __syncthreads();
+        // Memory-model bookkeeping, off the per-sweep critical path: the only cross-address
+        // ordering the protocol needs is "my re-arm of an inbox cell is performed before the
+        // neighbour's next write to it", HR_SLOTS sweeps later.  Every HR_FENCE_EVERY-th sweep
+        // each thread issues one gpu-scope fence here: it is the acquire fence for the cells this
+        // CTA just read and the release fence for everything it sends next, so re-arm ->
+        // (barrier) -> fence -> my data -> neighbour's read -> neighbour's fence -> its rewrite
+        // is a happens-before chain as long as 2*HR_FENCE_EVERY <= HR_SLOTS.
+        if (p.fences && (s % HR_FENCE_EVERY) == 0) __threadfence();
+        // ---- update: one (jj, k) column per thread, marching along ii; face cells also go to the
+        //      neighbours' inboxes (not after the last sweep: nobody would consume them)
+        const bool write_all = (s >= p.nsweeps - 1);
+        const bool send = (s < p.nsweeps);
+        const size_t out_slot = (size_t)(s % HR_SLOTS) * slot_sz;
+        for (int col = tid; col < ncols; col += HR_THREADS) {
+            const int jj = col / nk, kk = col - jj * nk;
+            const double *q = cur + ps + (jj + 1) * rs + 1 + kk;        // (ii = 0, jj, k)
+            double *o = nxt + ps + (jj + 1) * rs + 1 + kk;
+            double *g = gout + (long long)ilo * gps + (long long)(jlo + jj) * grs + 1 + kk;
+            double up = q[-ps], ce = q[0];
+#pragma unroll 2
+            for (int ii = 0; ii < nit; ++ii) {
+                const double dn = q[ps];
+                const double c2 = 2.0 * ce;
+                const double t1 = 0.125 * ((dn - c2) + up);
+                const double t2 = 0.125 * ((q[rs] - c2) + q[-rs]);
+                const double t3 = 0.125 * ((q[1] - c2) + q[-1]);
+                const double v = ((t1 + t2) + t3) + ce;
+                *o = v;
+                if (write_all) *g = v;
+                if (send) {
+                    // my face towards side X lands in the neighbour's opposite side
+                    if (ii == 0 && has_nb[0])
+                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[0] * box_sz + out_slot + 1 * side_sz + (size_t)jj * nk + kk), v);
+                    if (ii == nit - 1 && has_nb[1])
+                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[1] * box_sz + out_slot + 0 * side_sz + (size_t)jj * nk + kk), v);
+                    if (jj == 0 && has_nb[2])
+                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[2] * box_sz + out_slot + 3 * side_sz + (size_t)ii * nk + kk), v);
+                    if (jj == njt - 1 && has_nb[3])
+                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[3] * box_sz + out_slot + 2 * side_sz + (size_t)ii * nk + kk), v);
+                }
+                up = ce; ce = dn;
+                q += ps; o += ps; g += gps;
+            }
+        }
+        // the barrier at the top of the next sweep (after its receive phase) separates this
+        // update from the next one; receive only touches halo cells, which no update writes
     }
 }
+
+int g_resident_fences = 1;
+unsigned g_backoff_ns = 200;
 
 // Returns 1 if the resident kernel ran, 0 if the problem is not eligible, <0 on error.
 int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B) {
     if (nsweeps < 4 || n0 > 4096 || n1 > 4096 || n2 > 4096) return 0;
     const int sms = npb::st().sm_count;
     const int in0 = (int)n0 - 2, in1 = (int)n1 - 2;
-    // tiles: as square as possible, PI*PJ <= #SMs, each extent at most the interior size
+    // tiles: PI*PJ <= #SMs, minimise the largest tile's work plus its halo perimeter
     int PI = 1, PJ = 1;
     {
         long best = -1;
@@ -220,16 +261,14 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
             if (b > in1) b = in1;
             if (b < 1) continue;
             const int ta = (in0 + a - 1) / a, tb = (in1 + b - 1) / b;
-            // minimise the largest tile (work per sweep), then its perimeter
-            const long cost = (long)ta * tb * 1000 + (ta + tb);
+            const long cost = (long)ta * tb + 2L * (ta + tb);   // update work + halo traffic, in columns
             if (best < 0 || cost < best) { best = cost; PI = a; PJ = b; }
         }
     }
     const int ti_max = (in0 + PI - 1) / PI, tj_max = (in1 + PJ - 1) / PJ;
-    if (ti_max > 255 || tj_max > 255 || ti_max * tj_max > 1024) return 0;
     const size_t smem = (size_t)2 * (ti_max + 2) * (tj_max + 2) * n2 * sizeof(double);
-    // the kernel also has ~2 KB of static shared memory (row list)
-    if (smem + 4096 > npb::st().smem_optin) return 0;
+    if (smem + 2048 > npb::st().smem_optin) return 0;
+    if ((2 * ti_max + 2 * tj_max) * (n2 - 2) > HR_THREADS * HR_RECV) return 0;   // halo cells per CTA
     static size_t configured = 0;
     if (smem > configured) {
         if (cudaFuncSetAttribute(heat3d_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -242,13 +281,12 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
         return 0;
     }
     if ((long)per_sm * sms < (long)PI * PJ) return 0;      // all CTAs must be co-resident
-    unsigned *progress = (unsigned *)npb::workspace(1, 4096 * sizeof(unsigned));
-    if (!progress) return 0;
-    if (cudaMemsetAsync(progress, 0, (size_t)PI * PJ * sizeof(unsigned), npb::st().stream) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    ResidentParams rp{(int)n0, (int)n1, (int)n2, PI, PJ, ti_max, tj_max, (int)nsweeps, A, B, progress};
+    const int face_rows = ti_max > tj_max ? ti_max : tj_max;
+    const size_t box = (size_t)HR_SLOTS * 4 * face_rows * (n2 - 2);
+    unsigned long long *inbox = (unsigned long long *)npb::workspace(1, box * PI * PJ * sizeof(unsigned long long));
+    if (!inbox) return 0;
+    ResidentParams rp{(int)n0, (int)n1, (int)n2, PI, PJ, ti_max, tj_max, face_rows, (int)nsweeps, A, B, inbox,
+                      g_resident_fences, g_backoff_ns};
     void *args[] = {&rp};
     cudaError_t e = cudaLaunchCooperativeKernel((void *)heat3d_resident_kernel, dim3(PI * PJ), dim3(HR_THREADS),
                                                 args, smem, npb::st().stream);
@@ -436,14 +474,19 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     return 0;
 }
 
-int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 prefer the resident persistent kernel
+int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 resident if eligible, 3 temporally blocked passes
 int g_last_path = 0;   // 1 resident persistent kernel, 2 one launch per sweep, 3 temporally blocked passes
 
 }  // namespace
 
-// 0: size-based dispatch (default: temporally blocked passes for small grids, else streaming);
-// 1: always one launch per sweep; 2: prefer the on-chip resident persistent kernel
-extern "C" int npb_heat3d_set_mode(int mode) { g_mode = mode; return 0; }
+// 0: size-based dispatch (default: on-chip resident persistent kernel when the grid fits, else
+// one launch per sweep); 1: always one launch per sweep; 2: same as 0; 3: temporally blocked passes
+extern "C" int npb_heat3d_set_mode(int mode) {
+    g_resident_fences = (mode & 16) ? 0 : 1;
+    g_backoff_ns = (mode & 32) ? 50 : ((mode & 64) ? 800 : 200);   // +16: resident kernel without the per-sweep fences (experiments)
+    g_mode = mode & 15;
+    return 0;
+}
 // variant used by the last npb_heat3d_f64 call: 1 resident, 2 streaming, 3 temporally blocked
 extern "C" int npb_heat3d_last_path(void) { return g_last_path; }
 
@@ -464,12 +507,12 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
     NPB_ARG(n1 < (1LL << 31) && n2 < (1LL << 31) && n1 * n2 < (1LL << 40), "npb_heat3d_f64",
             "plane too large");
     if (tsteps <= 1 || n0 < 3 || n1 < 3 || n2 < 3) return 0;
-    if (g_mode == 2) {                       // on-chip resident persistent kernel (opt-in)
+    if (g_mode == 0 || g_mode == 2) {        // grids that fit on chip: resident persistent kernel
         const int r = try_resident(2 * (tsteps - 1), n0, n1, n2, A, B);
         if (r < 0) return -r;
         if (r == 1) { g_last_path = 1; return 0; }
     }
-    if (g_mode != 1) {                       // default: temporally blocked passes for small grids
+    if (g_mode == 3) {                       // temporally blocked passes (measured slower; kept for comparison)
         size_t smem = 0;
         const int T = tb_pick_tile(n0, n1, n2, &smem);
         if (T > 0) { g_last_path = 3; return run_tb(T, smem, 2 * (tsteps - 1), n0, n1, n2, A, B); }
