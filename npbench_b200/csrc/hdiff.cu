@@ -105,21 +105,21 @@ hdiff_march_kernel(int I, int JK, int K, long long in_pitch,   // in_pitch = (J+
 // level parallelism no longer depends on occupancy: one producer thread per
 // CTA streams whole input rows (and the matching coeff rows) into a ring of
 // shared-memory slots with cp.async.bulk (the TMA engine, 1-D bulk form),
-// completion tracked by mbarriers; 16 consumer warps take each row out of the
+// completion tracked by mbarriers; 15 consumer warps take each row out of the
 // ring exactly once -- 5 x 16-byte shared loads per thread (columns q-2..q+2)
 // into a register window that carries the rows still needed -- so a slot is
 // released the moment it has been read and all other slots are look-ahead
-// (up to 7 rows, ~140 KB in flight per SM).  Work is split statically: the
-// (j-tile, i) rows are cut into one contiguous range per SM, no tail wave.
+// (up to 7 rows, ~140 KB in flight per SM).  Work units (i-block, j-tile) are dealt
+// round-robin so that concurrently running CTAs share their halos through L2.
 // ---------------------------------------------------------------------------
 namespace ring {
 
 constexpr int MAX_SLOTS = 8;
-constexpr int CONSUMERS = 512;               // 16 warps, two adjacent k per thread
+constexpr int CONSUMERS = 480;               // 15 warps, two adjacent k per thread (512 threads => 128 regs each)
 constexpr int THREADS = CONSUMERS + 32;      // + producer warp
 
 struct Params {
-    int I, J, K, TJ, n_jtiles, n_slots;
+    int I, J, K, TJ, n_jtiles, RB, n_iblocks;
     int slot_in_elems;        // (TJ+4)*K
     int slot_elems;           // slot stride in doubles (in row + coeff row, 128-byte multiple)
     const double *in;
@@ -160,36 +160,76 @@ __device__ __forceinline__ double2 limitv(double2 a, double2 b, double2 hi, doub
     return make_double2(limit(a.x - b.x, hi.x - lo.x), limit(a.y - b.y, hi.y - lo.y));
 }
 
+// One consumer step: row `r` of the current unit has landed in `row`; W is the static position of
+// that row in the 4-deep circular register windows (W == (r - i0) & 3 after 4x unrolling), so no
+// register is ever moved: C/L/Rr hold columns q, q-1, q+1, LL/RR columns q-2, q+2, indexed by row & 3.
+template <int W>
+__device__ __forceinline__ void consume_row(const Params &p, const double *row, int r, int i0, int j0, int e0,
+                                            bool active, double2 (&C)[4], double2 (&Lw)[4], double2 (&Rw)[4],
+                                            double2 (&LL)[4], double2 (&RR)[4], double2 &lap_c, double2 &flx_m,
+                                            unsigned long long *empty_bar, int lane) {
+    const int K = p.K;
+    double2 cf = make_double2(0.0, 0.0);
+    if (active) {
+        const double *c = row + e0 + 2 * K;           // in[r, q, k] for this thread's (q, k) pair
+        C[W] = *reinterpret_cast<const double2 *>(c);
+        Lw[W] = *reinterpret_cast<const double2 *>(c - K);
+        Rw[W] = *reinterpret_cast<const double2 *>(c + K);
+        LL[W] = *reinterpret_cast<const double2 *>(c - 2 * K);
+        RR[W] = *reinterpret_cast<const double2 *>(c + 2 * K);
+        if (r - 4 >= i0) cf = *reinterpret_cast<const double2 *>(row + p.slot_in_elems + e0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar);            // this warp is done with the slot
+    // rows: r -> W, r-1 -> W+3, r-2 (centre row p) -> W+2, r-3 -> W+1   (indices mod 4)
+    constexpr int P2 = W, P1 = (W + 3) & 3, P0 = (W + 2) & 3, M1 = (W + 1) & 3;
+    const double2 lap_p = lap5v(C[P1], C[P2], C[P0], Rw[P1], Lw[P1]);      // lap(p+1, q)
+    const double2 lap_r = lap5v(Rw[P0], Rw[P1], Rw[M1], RR[P0], C[P0]);    // lap(p, q+1)
+    const double2 lap_l = lap5v(Lw[P0], Lw[P1], Lw[M1], C[P0], LL[P0]);    // lap(p, q-1)
+    const double2 flx_c = limitv(lap_p, lap_c, C[P1], C[P0]);
+    const double2 fly_c = limitv(lap_r, lap_c, Rw[P0], C[P0]);
+    const double2 fly_m = limitv(lap_c, lap_l, C[P0], Lw[P0]);
+    if (active && r - 4 >= i0) {
+        double2 res;
+        res.x = C[P0].x - cf.x * (((flx_c.x - flx_m.x) + fly_c.x) - fly_m.x);
+        res.y = C[P0].y - cf.y * (((flx_c.y - flx_m.y) + fly_c.y) - fly_m.y);
+        double2 *o = reinterpret_cast<double2 *>(p.out + ((long long)(r - 4) * p.J + j0) * K + e0);
+        __stcs(o, res);
+    }
+    lap_c = lap_p; flx_m = flx_c;
+}
+
+template <int NS>
 __global__ void __launch_bounds__(THREADS, 1)
 hdiff_ring_kernel(Params p) {
     extern __shared__ __align__(128) double ring_mem[];
-    __shared__ __align__(8) unsigned long long full_bar[MAX_SLOTS], empty_bar[MAX_SLOTS];
+    __shared__ __align__(8) unsigned long long full_bar[NS], empty_bar[NS];
 
     const int tid = threadIdx.x;
     const int K = p.K, I = p.I, J = p.J;
     if (tid == 0) {
-        for (int s = 0; s < p.n_slots; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMERS / 32); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // static partition of the n_jtiles * I tile-rows (j-tile major) over the CTAs
-    const long long W = (long long)p.n_jtiles * I;
-    long long w = W * blockIdx.x / gridDim.x;
-    const long long w_end = W * (blockIdx.x + 1) / gridDim.x;
+    // Work units = (i-block of RB rows, j-tile), j-tile fastest, dealt round-robin to the CTAs:
+    // at any moment the CTAs work on neighbouring j-tiles of the same i-block, so the j-halo
+    // columns and the i-halo rows that two units share are fetched from DRAM once and hit L2.
+    const int n_units = p.n_iblocks * p.n_jtiles;
     unsigned job = 0;     // ring position, identical sequence in producer and consumers
 
     if (tid >= CONSUMERS) {
         // ------------------------------ producer (one elected thread) -------------
         if (tid == CONSUMERS) {
-            while (w < w_end) {
-                const int jt = (int)(w / I), i0 = (int)(w - (long long)jt * I);
-                const int i1 = (int)min((long long)I, i0 + (w_end - w));
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int ib = u / p.n_jtiles, jt = u - ib * p.n_jtiles;
+                const int i0 = ib * p.RB, i1 = min(I, i0 + p.RB);
                 const int j0 = jt * p.TJ, tjc = min(p.TJ, J - j0);
                 const unsigned bytes_in = (unsigned)((tjc + 4) * K) * 8u, bytes_c = (unsigned)(tjc * K) * 8u;
                 for (int r = i0; r < i1 + 4; ++r, ++job) {
-                    const int slot = job % p.n_slots;
-                    const unsigned ph = (job / p.n_slots) & 1u;
+                    const int slot = job & (NS - 1);
+                    const unsigned ph = (job / NS) & 1u;
                     mbar_wait(&empty_bar[slot], ph ^ 1u);           // slot drained by all consumer warps
                     const bool has_c = (r - 4 >= i0);
                     double *dst = ring_mem + (size_t)slot * p.slot_elems;
@@ -199,7 +239,6 @@ hdiff_ring_kernel(Params p) {
                         bulk_g2s(dst + p.slot_in_elems, p.coeff + ((long long)(r - 4) * J + j0) * K, bytes_c,
                                  &full_bar[slot]);
                 }
-                w += i1 - i0;
             }
         }
         return;
@@ -208,57 +247,28 @@ hdiff_ring_kernel(Params p) {
     // ---------------------------------- consumers ---------------------------------
     const int e0 = 2 * tid;                       // first of the two adjacent flattened (j,k) elements
     const int lane = tid & 31;
-    while (w < w_end) {
-        const int jt = (int)(w / I), i0 = (int)(w - (long long)jt * I);
-        const int i1 = (int)min((long long)I, i0 + (w_end - w));
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int ib = u / p.n_jtiles, jt = u - ib * p.n_jtiles;
+        const int i0 = ib * p.RB, i1 = min(I, i0 + p.RB);
         const int j0 = jt * p.TJ, tjc = min(p.TJ, J - j0);
         const bool active = e0 < tjc * K;
         const double2 z = make_double2(0.0, 0.0);
-        double2 c_m1 = z, c_0 = z, c_p1 = z, c_p2 = z;
-        double2 l_m1 = z, l_0 = z, l_p1 = z, l_p2 = z, r_m1 = z, r_0 = z, r_p1 = z, r_p2 = z;
-        double2 ll_0 = z, ll_p1 = z, ll_p2 = z, rr_0 = z, rr_p1 = z, rr_p2 = z;
+        double2 C[4] = {z, z, z, z}, Lw[4] = {z, z, z, z}, Rw[4] = {z, z, z, z}, LL[4] = {z, z, z, z},
+                RR[4] = {z, z, z, z};
         double2 lap_c = z, flx_m = z;
-        for (int r = i0; r < i1 + 4; ++r, ++job) {
-            const int slot = job % p.n_slots;
-            const unsigned ph = (job / p.n_slots) & 1u;
-            mbar_wait(&full_bar[slot], ph);
-            const double *row = ring_mem + (size_t)slot * p.slot_elems;
-            double2 v_c = z, v_l = z, v_r = z, v_ll = z, v_rr = z, cf = z;
-            if (active) {
-                const double *c = row + e0 + 2 * K;           // in[r, q, k] for this thread's (q, k)
-                v_c = *reinterpret_cast<const double2 *>(c);
-                v_l = *reinterpret_cast<const double2 *>(c - K);
-                v_r = *reinterpret_cast<const double2 *>(c + K);
-                v_ll = *reinterpret_cast<const double2 *>(c - 2 * K);
-                v_rr = *reinterpret_cast<const double2 *>(c + 2 * K);
-                if (r - 4 >= i0) cf = *reinterpret_cast<const double2 *>(row + p.slot_in_elems + e0);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);     // this warp is done with the slot
-            // roll the register window: row r enters as the "+2" entries (centre row p = r - 2)
-            c_m1 = c_0; c_0 = c_p1; c_p1 = c_p2; c_p2 = v_c;
-            l_m1 = l_0; l_0 = l_p1; l_p1 = l_p2; l_p2 = v_l;
-            r_m1 = r_0; r_0 = r_p1; r_p1 = r_p2; r_p2 = v_r;
-            ll_0 = ll_p1; ll_p1 = ll_p2; ll_p2 = v_ll;
-            rr_0 = rr_p1; rr_p1 = rr_p2; rr_p2 = v_rr;
-            // same arithmetic as the marching kernel; values are meaningful once enough rows
-            // of the segment have arrived, and only then stored
-            const double2 lap_p = lap5v(c_p1, c_p2, c_0, r_p1, l_p1);     // lap(p+1, q)
-            const double2 lap_r = lap5v(r_0, r_p1, r_m1, rr_0, c_0);      // lap(p, q+1)
-            const double2 lap_l = lap5v(l_0, l_p1, l_m1, c_0, ll_0);      // lap(p, q-1)
-            const double2 flx_c = limitv(lap_p, lap_c, c_p1, c_0);
-            const double2 fly_c = limitv(lap_r, lap_c, r_0, c_0);
-            const double2 fly_m = limitv(lap_c, lap_l, c_0, l_0);
-            if (active && r - 4 >= i0) {
-                double2 res;
-                res.x = c_0.x - cf.x * (((flx_c.x - flx_m.x) + fly_c.x) - fly_m.x);
-                res.y = c_0.y - cf.y * (((flx_c.y - flx_m.y) + fly_c.y) - fly_m.y);
-                double2 *o = reinterpret_cast<double2 *>(p.out + ((long long)(r - 4) * J + j0) * K + e0);
-                __stcs(o, res);
-            }
-            lap_c = lap_p; flx_m = flx_c;
+        const int r_end = i1 + 4;
+#define NPB_HD_STEP(WPOS)                                                                              \
+        if (r < r_end) {                                                                               \
+            const int slot = job & (NS - 1);                                                           \
+            mbar_wait(&full_bar[slot], (job / NS) & 1u);                                               \
+            consume_row<WPOS>(p, ring_mem + (size_t)slot * p.slot_elems, r, i0, j0, e0, active, C, Lw, \
+                              Rw, LL, RR, lap_c, flx_m, &empty_bar[slot], lane);                       \
+            ++r; ++job;                                                                                \
         }
-        w += i1 - i0;
+        for (int r = i0; r < r_end;) {
+            NPB_HD_STEP(0) NPB_HD_STEP(1) NPB_HD_STEP(2) NPB_HD_STEP(3)
+        }
+#undef NPB_HD_STEP
     }
 }
 
@@ -275,25 +285,47 @@ int try_ring(int64_t I, int64_t J, int64_t K, const double *in, double *out, con
     if (TJ < 1) return 0;
     const int n_jtiles = (int)((J + TJ - 1) / TJ);
     const int sms = npb::st().sm_count;
-    const long long W = (long long)n_jtiles * I;
-    if (!force && W < 16LL * sms) return 0;                           // too little work per SM
+    if (!force && (long long)n_jtiles * I < 16LL * sms) return 0;     // too little work per SM
     const int slot_in = (int)((TJ + 4) * K);
     int slot_elems = slot_in + (int)(TJ * K);
     slot_elems = (slot_elems + 15) & ~15;
     const size_t slot_bytes = (size_t)slot_elems * sizeof(double);
-    int n_slots = (int)((npb::st().smem_optin - 1024) / slot_bytes);
-    if (n_slots > ring::MAX_SLOTS) n_slots = ring::MAX_SLOTS;
-    if (n_slots < 3) return 0;
-    const size_t smem = slot_bytes * n_slots;
-    static size_t configured = 0;
-    if (smem > configured) {
-        if (cudaFuncSetAttribute(ring::hdiff_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-            cudaSuccess) { cudaGetLastError(); return 0; }
-        configured = smem;
+    const int fit = (int)((npb::st().smem_optin - 1024) / slot_bytes);
+    const int n_slots = fit >= 8 ? 8 : (fit >= 4 ? 4 : 0);
+    if (n_slots == 0) return 0;
+    // rows per i-block: best load balance of the round-robin deal, then the longest block
+    int RB = 8;
+    {
+        double best = -1.0;
+        for (int rb = 8; rb <= 64; ++rb) {
+            const long long units = (long long)((I + rb - 1) / rb) * n_jtiles;
+            const long long rounds = (units + sms - 1) / sms;
+            const double eff = (double)units / (double)(rounds * sms) * ((double)rb / (rb + 4.0) * 0.25 + 0.75);
+            if (eff >= best) { best = eff; RB = rb; }
+        }
+        if (RB > I) RB = (int)I;
     }
-    ring::Params rp{(int)I, (int)J, (int)K, TJ, n_jtiles, n_slots, slot_in, slot_elems, in, out, coeff};
-    const int grid = (int)(W < sms ? W : sms);
-    ring::hdiff_ring_kernel<<<grid, ring::THREADS, smem, npb::st().stream>>>(rp);
+    const int n_iblocks = (int)((I + RB - 1) / RB);
+    const size_t smem = slot_bytes * n_slots;
+    ring::Params rp{(int)I, (int)J, (int)K, TJ, n_jtiles, RB, n_iblocks, slot_in, slot_elems, in, out, coeff};
+    const long long units = (long long)n_iblocks * n_jtiles;
+    const int grid = (int)(units < sms ? units : sms);
+    static size_t configured8 = 0, configured4 = 0;
+    if (n_slots == 8) {
+        if (smem > configured8) {
+            if (cudaFuncSetAttribute(ring::hdiff_ring_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                cudaSuccess) { cudaGetLastError(); return 0; }
+            configured8 = smem;
+        }
+        ring::hdiff_ring_kernel<8><<<grid, ring::THREADS, smem, npb::st().stream>>>(rp);
+    } else {
+        if (smem > configured4) {
+            if (cudaFuncSetAttribute(ring::hdiff_ring_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+                cudaSuccess) { cudaGetLastError(); return 0; }
+            configured4 = smem;
+        }
+        ring::hdiff_ring_kernel<4><<<grid, ring::THREADS, smem, npb::st().stream>>>(rp);
+    }
     return 1;
 }
 
