@@ -123,6 +123,8 @@ int npb_hdiff_last_path(void);           /* 1 marching, 2 ring */
 int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
                  const double *wcon, const double *u_pos, const double *utens, double dtr_stage);
 
+int npb_vadv_set_trace(void *dev_buf);   /* profiling aid: per-group phase timestamps (ngroups*8 u64), NULL = off */
+
 /* ---- the same five calls on HOST buffers (copy in, run, copy outputs back,
  *      synchronise): the NumPy-signature call of bench_info/<b>.json ------- */
 int npb_jacobi2d_f64_host(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B);

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "npb_hdiff_set_mode": (_int, [_int]),
     "npb_hdiff_last_path": (_int, []),
     "npb_vadv_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _dbl]),
+    "npb_vadv_set_trace": (_int, [_vp]),
     "npb_jacobi2d_f64_host": (_int, [_i64, _i64, _i64, _vp, _vp]),
     "npb_heat3d_f64_host": (_int, [_i64, _i64, _i64, _i64, _vp, _vp]),
     "npb_fdtd2d_f64_host": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),

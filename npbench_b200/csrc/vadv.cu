@@ -5,25 +5,31 @@
 // npbench/benchmarks/weather_stencils/vadv/vadv_numpy.py:9-78.
 //
 // Layout problem: arrays are (I,J,K) with K -- the recurrence axis --
-// contiguous, so "one column per thread" has a lane stride of K*8 bytes.
-// Design: one small CTA (4 warps) owns NC <= 32 consecutive columns (one contiguous
-// NC*K*8-byte chunk per array) and runs four phases over a shared-memory tile
-// [K][NCP] (NCP odd => conflict-free both for lanes-along-k and
+// contiguous, so "one column per thread" has a lane stride of K*8 bytes, while
+// the Thomas recurrence is a serial IEEE-divide chain (~150 cycles per level).
+// Design: a column group (NC <= 32 consecutive columns = one contiguous
+// NC*K*8-byte chunk per array) goes through four phases over a shared-memory
+// tile [K][NCP] (NCP odd => conflict-free for lanes-along-k and for
 // lanes-along-column accesses):
 //   A  lanes along k, coalesced global reads of all five inputs; everything
-//      that does not depend on the recurrence is computed here:
-//      a_k (= acol = as) and the full right-hand side dcol_k before the
-//      Thomas step; stored transposed into the tile;
-//   B  lanes along columns: Thomas forward sweep (the serial divide chain),
-//      overwriting the tile with ccol_k, dcol_k;
+//      that does not depend on the recurrence is computed here: a_k (= acol =
+//      as) and the full right-hand side dcol_k before the Thomas step; stored
+//      transposed into the tile;
+//   B  lanes along columns: Thomas forward sweep, tile <- ccol_k, dcol_k;
 //   C  lanes along columns: back-substitution, tile <- datacol_k;
 //   D  lanes along k: utens_stage = dtr*(datacol - u_pos), coalesced store.
-// All HBM traffic is coalesced; ccol/dcol never leave the SM (the reference
-// allocates them as full (I,J,K) temporaries, vadv_numpy.py:11-12).
-// All warps of the CTA take part in the coalesced phases A and D (memory-level
-// parallelism), the first NC threads run the serial phases B and C.  Several
-// CTAs per SM are resident (as many as shared memory allows), so phase A/D
-// traffic of one overlaps the latency-bound B/C of the others.
+// ccol/dcol never leave the SM (the reference allocates them as full (I,J,K)
+// temporaries, vadv_numpy.py:11-12).
+//
+// Scheduling (measured, profiles/): A and D are HBM phases that need many warps
+// in flight; B+C is a latency chain that needs exactly one warp per group and
+// keeps one SM sub-partition's FP64 pipe busy.  So ONE persistent CTA per SM
+// owns up to three tiles and is warp specialised: warps 13..15 (three different
+// sub-partitions, highest issue priority) are the solvers of tiles 0..2; warps 0..12 are movers that
+// run phase D of a solved tile and phase A of its next group, tile after tile.
+// Tiles hand over through mbarriers (loaded[t], solved[t]); no __syncthreads in
+// the steady state, and HBM traffic of one tile overlaps the solves of the
+// others.
 //
 // Identities used (exact in binary64): BET_M == BET_P == 0.5, hence
 // as == acol and cs == ccol-before-division; and gcv_k*0.5 == -(gav_{k+1}*0.5)
@@ -33,48 +39,67 @@
 
 namespace {
 
-constexpr int VA_WARPS = 4;                 // warps per CTA: all of them load/store (phases A, D),
-constexpr int VA_THREADS = 32 * VA_WARPS;   // the first NC threads run the per-column solve (B, C)
-constexpr int VA_U = 6;    // phase-A work items loaded per batch
-constexpr int VD_U = 10;   // phase-D work items loaded per batch
+constexpr int VA_TILES = 3;                              // tiles (column groups in flight) per CTA
+constexpr int VA_WARPS = 16;
+constexpr int VA_THREADS = 32 * VA_WARPS;
+constexpr int VA_MOVERS = VA_WARPS - VA_TILES;           // warps 0..12 move, warps 13..15 solve
+constexpr int VA_U = 2;                                  // phase-A items per mover batch (11 loads each)
+constexpr int VD_U = 6;                                  // phase-D items per mover batch (1 load each)
 
 struct VadvParams {
     long long ncols;      // I*J
+    long long ngroups;
     int K;
     int J;
-    int NC;               // columns per CTA
+    int NC;               // columns per group
     int NCP;              // padded (odd) tile row stride
+    int ntiles;           // tiles actually used (<= VA_TILES)
     double dtr;
     double *utens_stage;
     const double *u_stage, *wcon, *u_pos, *utens;
+    unsigned long long *trace;   // profiling aid: [ngroups][8] globaltimer stamps, or NULL
 };
 
-__global__ void __launch_bounds__(VA_THREADS, 4)
-vadv_warp_kernel(VadvParams p) {
-    extern __shared__ double tile[];
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// `backoff_ns` > 0: sleep between polls so that waiting warps do not steal issue slots from
+// the solver warps that share their sub-partition.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity, unsigned backoff_ns = 0) {
+    unsigned done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
+}
+
+// ---------------- phase A (mover warps, lanes along k) -----------------------
+// Work items = (column, 32-level block), dealt cyclically to the mover warps and
+// processed in batches of VA_U; all loads of a batch are issued before the first use.  Neighbour levels
+// use clamped indices and selects instead of branches.
+__device__ __forceinline__ void phase_a(const VadvParams &p, double *tA, double *tD, long long col0, int nc,
+                                        int mover, int lane) {
     const int K = p.K, NCP = p.NCP;
-    double *tA = tile;                     // a_k   -> ccol_k
-    double *tD = tile + (size_t)K * NCP;   // dc_k  -> dcol_k -> datacol_k
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long col0 = (long long)blockIdx.x * p.NC;
-    const int nc = (int)min((long long)p.NC, p.ncols - col0);
     const double dtr = p.dtr;
     const long long JK = (long long)p.J * K;
-
-    // ---------------- phase A: lanes along k ------------------------------
-    // Work items = (column, 32-level block); VA_U items are loaded as one batch so that
-    // ~10*VA_U independent loads per lane are in flight (the warp is alone in its CTA, so
-    // memory-level parallelism has to come from the instruction stream).  Neighbour
-    // levels use clamped indices and selects instead of branches.
     const int nkb = (K + 31) >> 5;
     const int items = nc * nkb;
-    for (int it0 = warp * VA_U; it0 < items; it0 += VA_WARPS * VA_U) {
+    // item `it` belongs to mover (it % VA_MOVERS) in phase A and in phase D alike
+    for (int it0 = mover; it0 < items; it0 += VA_MOVERS * VA_U) {
         double r_um[VA_U], r_uc[VA_U], r_un[VA_U], r_wc[VA_U], r_wn[VA_U], r_d0a[VA_U], r_ut[VA_U], r_uo[VA_U];
         int r_k[VA_U], r_cc[VA_U];
 #pragma unroll
         for (int u = 0; u < VA_U; ++u) {
-            const int it = min(it0 + u, items - 1);
+            const int it = min(it0 + u * VA_MOVERS, items - 1);
             const int cc = it / nkb;
             const int k = min(((it - cc * nkb) << 5) + lane, K - 1);
             const int km = max(k - 1, 0), kp = min(k + 1, K - 1);
@@ -103,77 +128,88 @@ vadv_warp_kernel(VadvParams p) {
             const double t_hi = cs * (r_un[u] - r_uc[u]);
             // :23 (-cs)*(...) == -(cs*(...)) exactly ; :44-46 ; :62
             const double corr = (k == 0) ? -t_hi : ((k < K - 1) ? (t_lo - t_hi) : t_lo);
-            if (it0 + u < items && ((it0 + u - r_cc[u] * nkb) << 5) + lane < K) {
+            const int itu = it0 + u * VA_MOVERS;
+            if (itu < items && ((itu - r_cc[u] * nkb) << 5) + lane < K) {
                 tA[k * NCP + r_cc[u]] = a;
                 tD[k * NCP + r_cc[u]] = d0 + corr;
             }
         }
     }
-    __syncthreads();
+}
 
-    // ---------------- phase B + C: lanes along columns --------------------
-    if (threadIdx.x < nc) {
-        double *cA = tA + threadIdx.x;
-        double *cD = tD + threadIdx.x;
-        // k = 0 : vadv_numpy.py:19-30   ccol = gcv*BET_P == -a_1
-        double a_cur = cA[NCP];                              // a_1
-        double a_nxt = cA[min(2, K - 1) * NCP];              // a_2
-        double dc_cur = cD[min(1, K - 1) * NCP];             // dc_1
-        double ccv = -a_cur;
-        double bcol = dtr - ccv;
-        double divided = 1.0 / bcol;
-        double c_prev = ccv * divided;
-        double d_prev = cD[0] * divided;
-        cA[0] = c_prev;
-        cD[0] = d_prev;
-        // 1 <= k <= K-2 : :32-53.  Operands of level k+1 are fetched before the stores of
-        // level k, so their shared-memory latency hides under the divide chain.
-        for (int k = 1; k < K - 1; ++k) {
-            const double a_pf = cA[min(k + 2, K - 1) * NCP];
-            const double dc_pf = cD[(k + 1) * NCP];
-            const double a = a_cur;
-            ccv = -a_nxt;
-            bcol = (dtr - a) - ccv;
-            divided = 1.0 / (bcol - c_prev * a);
-            c_prev = ccv * divided;
-            d_prev = (dc_cur - d_prev * a) * divided;
-            cA[k * NCP] = c_prev;
-            cD[k * NCP] = d_prev;
-            a_cur = a_nxt; a_nxt = a_pf; dc_cur = dc_pf;
-        }
-        {   // k = K-1 : :55-68
-            const double a = a_cur;
-            bcol = dtr - a;
-            divided = 1.0 / (bcol - c_prev * a);
-            d_prev = (dc_cur - d_prev * a) * divided;
-            cD[(K - 1) * NCP] = d_prev;       // datacol_{K-1} = dcol_{K-1}  (:70-73)
-        }
-        // back-substitution : :75-78
-        double x = d_prev;
-        double c_k = (K >= 2) ? cA[(K - 2) * NCP] : 0.0, d_k = cD[(K - 2) * NCP];
-        for (int k = K - 2; k >= 0; --k) {
-            const int kn = max(k - 1, 0);
-            const double c_pf = cA[kn * NCP], d_pf = cD[kn * NCP];
-            x = d_k - c_k * x;
-            cD[k * NCP] = x;
-            c_k = c_pf; d_k = d_pf;
-        }
+// ---------------- phases B + C (one solver warp, lanes along columns) --------
+__device__ __forceinline__ void phase_bc(const VadvParams &p, double *tA, double *tD, int nc, int lane) {
+    const int K = p.K, NCP = p.NCP;
+    const double dtr = p.dtr;
+    if (lane >= nc) return;
+    double *cA = tA + lane;
+    double *cD = tD + lane;
+    // k = 0 : vadv_numpy.py:19-30   ccol = gcv*BET_P == -a_1
+    double a_cur = cA[NCP];                              // a_1
+    double a_nxt = cA[min(2, K - 1) * NCP];              // a_2
+    double dc_cur = cD[min(1, K - 1) * NCP];             // dc_1
+    double ccv = -a_cur;
+    double bcol = dtr - ccv;
+    double divided = 1.0 / bcol;
+    double c_prev = ccv * divided;
+    double d_prev = cD[0] * divided;
+    cA[0] = c_prev;
+    cD[0] = d_prev;
+    // 1 <= k <= K-2 : :32-53.  Operands of level k+1 are fetched before the stores of
+    // level k, so their shared-memory latency hides under the divide chain.
+    for (int k = 1; k < K - 1; ++k) {
+        const double a_pf = cA[min(k + 2, K - 1) * NCP];
+        const double dc_pf = cD[(k + 1) * NCP];
+        const double a = a_cur;
+        ccv = -a_nxt;
+        bcol = (dtr - a) - ccv;
+        divided = 1.0 / (bcol - c_prev * a);
+        c_prev = ccv * divided;
+        d_prev = (dc_cur - d_prev * a) * divided;
+        cA[k * NCP] = c_prev;
+        cD[k * NCP] = d_prev;
+        a_cur = a_nxt; a_nxt = a_pf; dc_cur = dc_pf;
     }
-    __syncthreads();
+    {   // k = K-1 : :55-68
+        const double a = a_cur;
+        bcol = dtr - a;
+        divided = 1.0 / (bcol - c_prev * a);
+        d_prev = (dc_cur - d_prev * a) * divided;
+        cD[(K - 1) * NCP] = d_prev;       // datacol_{K-1} = dcol_{K-1}  (:70-73)
+    }
+    // back-substitution : :75-78
+    double x = d_prev;
+    double c_k = cA[(K - 2) * NCP], d_k = cD[(K - 2) * NCP];
+    for (int k = K - 2; k >= 0; --k) {
+        const int kn = max(k - 1, 0);
+        const double c_pf = cA[kn * NCP], d_pf = cD[kn * NCP];
+        x = d_k - c_k * x;
+        cD[k * NCP] = x;
+        c_k = c_pf; d_k = d_pf;
+    }
+}
 
-    // ---------------- phase D: lanes along k ------------------------------
-    for (int it0 = warp * VD_U; it0 < items; it0 += VA_WARPS * VD_U) {
+// ---------------- phase D (mover warps, lanes along k) -----------------------
+// Same item -> warp map as phase A: a mover warp reads in D exactly the tile cells it
+// overwrites in the following phase A of the same tile, so D -> A needs no barrier.
+__device__ __forceinline__ void phase_d(const VadvParams &p, const double *tD, long long col0, int nc, int mover,
+                                        int lane) {
+    const int K = p.K, NCP = p.NCP;
+    const double dtr = p.dtr;
+    const int nkb = (K + 31) >> 5;
+    const int items = nc * nkb;
+    for (int it0 = mover; it0 < items; it0 += VA_MOVERS * VD_U) {
         double r_up[VD_U];
 #pragma unroll
         for (int u = 0; u < VD_U; ++u) {
-            const int it = min(it0 + u, items - 1);
+            const int it = min(it0 + u * VA_MOVERS, items - 1);
             const int cc = it / nkb;
             const int k = min(((it - cc * nkb) << 5) + lane, K - 1);
             r_up[u] = __ldg(p.u_pos + (col0 + cc) * K + k);
         }
 #pragma unroll
         for (int u = 0; u < VD_U; ++u) {
-            const int it = it0 + u;
+            const int it = it0 + u * VA_MOVERS;
             const int cc = min(it, items - 1) / nkb;
             const int k = ((it - cc * nkb) << 5) + lane;
             if (it < items && k < K)
@@ -182,25 +218,106 @@ vadv_warp_kernel(VadvParams p) {
     }
 }
 
-// Pick NC (columns per CTA).  The forward sweep is a serial divide chain per
-// column; one warp per SM sub-partition already keeps the FP64 pipe ~85% busy, so the goal
-// is to maximise columns resident on up to 4 warps per SM (more CTAs only help overlap the
-// load/store phases), with full-width warps preferred when shared memory allows.
-void pick_geometry(int K, size_t smem_per_sm, size_t smem_per_block, int *NC, int *NCP, size_t *bytes) {
-    long best_score = -1;
-    *NC = 0;
-    for (int nc = 32; nc >= 8; --nc) {
-        const int ncp = nc | 1;
-        const size_t b = (size_t)2 * K * ncp * sizeof(double);
-        if (b > smem_per_block) continue;
-        long ctas = (long)(smem_per_sm / (b + 1024));
-        if (ctas > 8) ctas = 8;
-        const long score = (ctas < 4 ? ctas : 4) * nc * 16 + ctas;   // columns on <=4 warps, then more CTAs
-        if (score > best_score) { best_score = score; *NC = nc; *NCP = ncp; *bytes = b; }
+__device__ __forceinline__ void stamp(const VadvParams &p, long long g, int slot, bool who) {
+    if (p.trace && who) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        p.trace[g * 8 + slot] = t;
     }
 }
 
+__global__ void __launch_bounds__(VA_THREADS, 1)
+vadv_pipeline_kernel(VadvParams p) {
+    extern __shared__ double tiles[];
+    __shared__ __align__(8) unsigned long long loaded[VA_TILES], solved[VA_TILES];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const size_t tile_sz = (size_t)2 * p.K * p.NCP;          // doubles per tile: a/ccol plane + dcol plane
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < VA_TILES; ++t) { mbar_init(&loaded[t], VA_MOVERS); mbar_init(&solved[t], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // tile t of CTA b works on groups  b*ntiles + t + n * (ntiles * gridDim.x),  n = 0, 1, ...
+    const long long stride = (long long)p.ntiles * gridDim.x;
+    const long long first = (long long)blockIdx.x * p.ntiles;
+
+    // Measured (tools/vadv_trace.py): a solve takes 12-13 us when its sub-partition is otherwise
+    // idle and ~21 us when mover warps share it (FP64 pipe / issue slots); giving the movers only
+    // sub-partition 0 fixes the solve but starves phases A/D (4 movers).  Next step: feed phase A
+    // with TMA bulk copies so that few mover warps suffice.
+    if (warp >= VA_MOVERS) {
+        // ------------------------------- solver of tile `warp - VA_MOVERS` ---------
+        const int t = warp - VA_MOVERS;
+        if (t >= p.ntiles) return;
+        double *tA = tiles + t * tile_sz, *tD = tA + (size_t)p.K * p.NCP;
+        unsigned n = 0;
+        for (long long g = first + t; g < p.ngroups; g += stride, ++n) {
+            const int nc = (int)min((long long)p.NC, p.ncols - g * p.NC);
+            mbar_wait(&loaded[t], n & 1u);
+            stamp(p, g, 2, lane == 0);
+            phase_bc(p, tA, tD, nc, lane);
+            __syncwarp();
+            stamp(p, g, 3, lane == 0);
+            if (lane == 0) mbar_arrive(&solved[t]);
+        }
+        return;
+    }
+
+    // ----------------------------------- movers ------------------------------------
+    const int mover = warp;
+    for (int t = 0; t < p.ntiles; ++t) {                      // prologue: first group of every tile
+        const long long g = first + t;
+        if (g >= p.ngroups) break;
+        double *tA = tiles + t * tile_sz, *tD = tA + (size_t)p.K * p.NCP;
+        stamp(p, g, 0, mover == 0 && lane == 0);
+        phase_a(p, tA, tD, g * p.NC, (int)min((long long)p.NC, p.ncols - g * p.NC), mover, lane);
+        __syncwarp();
+        stamp(p, g, 1, mover == 0 && lane == 0);
+        if (lane == 0) mbar_arrive(&loaded[t]);
+    }
+    for (unsigned n = 0;; ++n) {
+        bool any = false;
+        for (int t = 0; t < p.ntiles; ++t) {
+            const long long g = first + t + (long long)n * stride;
+            if (g >= p.ngroups) continue;
+            any = true;
+            double *tA = tiles + t * tile_sz, *tD = tA + (size_t)p.K * p.NCP;
+            mbar_wait(&solved[t], n & 1u, 256);
+            stamp(p, g, 4, mover == 0 && lane == 0);
+            phase_d(p, tD, g * p.NC, (int)min((long long)p.NC, p.ncols - g * p.NC), mover, lane);
+            stamp(p, g, 5, mover == 0 && lane == 0);
+            const long long g2 = g + stride;
+            if (g2 < p.ngroups) {
+                stamp(p, g2, 0, mover == 0 && lane == 0);
+                phase_a(p, tA, tD, g2 * p.NC, (int)min((long long)p.NC, p.ncols - g2 * p.NC), mover, lane);
+                __syncwarp();
+                stamp(p, g2, 1, mover == 0 && lane == 0);
+                if (lane == 0) mbar_arrive(&loaded[t]);
+            }
+        }
+        if (!any) break;
+    }
+}
+
+// Geometry: as many tiles (<= 3) as possible with the widest column groups that fit.
+bool pick_geometry(int K, size_t smem_per_block, int *ntiles, int *NC, int *NCP, size_t *bytes) {
+    for (int nt = VA_TILES; nt >= 1; --nt)
+        for (int nc = 32; nc >= (nt > 1 ? 12 : 1); --nc) {
+            const int ncp = nc | 1;
+            const size_t b = (size_t)nt * 2 * K * ncp * sizeof(double);
+            if (b + 256 <= smem_per_block) { *ntiles = nt; *NC = nc; *NCP = ncp; *bytes = b; return true; }
+        }
+    return false;
+}
+
+unsigned long long *g_trace = nullptr;
+
 }  // namespace
+
+// profiling aid: device buffer of ngroups*8 u64 receiving per-group phase timestamps (NULL = off)
+extern "C" int npb_vadv_set_trace(void *dev_buf) { g_trace = (unsigned long long *)dev_buf; return 0; }
 
 extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage,
                             const double *u_stage, const double *wcon, const double *u_pos,
@@ -210,24 +327,29 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     NPB_ARG(K >= 2, "npb_vadv_f64", "K must be >= 2 (the reference indexes level k+1 at k=0)");
     if (I == 0 || J == 0) return 0;
     NPB_ARG(K < (1 << 20), "npb_vadv_f64", "K too large");
-    int NC = 0, NCP = 0;
+    int ntiles = 0, NC = 0, NCP = 0;
     size_t bytes = 0;
-    const size_t per_block = npb::st().smem_optin;
-    pick_geometry((int)K, per_block + 1024, per_block, &NC, &NCP, &bytes);
-    NPB_ARG(NC > 0, "npb_vadv_f64", "K too large for the shared-memory column tile");
+    NPB_ARG(pick_geometry((int)K, npb::st().smem_optin, &ntiles, &NC, &NCP, &bytes), "npb_vadv_f64",
+            "K too large for the shared-memory column tile");
     static size_t configured = 0;
     if (bytes > configured) {
-        NPB_CUDA(cudaFuncSetAttribute(vadv_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)per_block));
-        configured = per_block;
+        NPB_CUDA(cudaFuncSetAttribute(vadv_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured = bytes;
     }
     VadvParams p;
     p.ncols = I * J; p.K = (int)K; p.J = (int)J; p.NC = NC; p.NCP = NCP; p.dtr = dtr_stage;
     p.utens_stage = utens_stage; p.u_stage = u_stage; p.wcon = wcon; p.u_pos = u_pos; p.utens = utens;
-    const long long nblk = (p.ncols + NC - 1) / NC;
-    NPB_ARG(nblk < (1LL << 31), "npb_vadv_f64", "too many columns");
-    vadv_warp_kernel<<<(unsigned)nblk, VA_THREADS, bytes, npb::st().stream>>>(p);
-    NPB_CHECK_LAUNCH("vadv_warp_kernel");
+    p.ngroups = (p.ncols + NC - 1) / NC;
+    NPB_ARG(p.ngroups < (1LL << 31), "npb_vadv_f64", "too many columns");
+    // few groups: fewer tiles per CTA so that every SM gets work
+    const int sms = npb::st().sm_count;
+    while (ntiles > 1 && p.ngroups < (long long)ntiles * sms) --ntiles;
+    p.ntiles = ntiles;
+    p.trace = g_trace;
+    long long grid = (p.ngroups + ntiles - 1) / ntiles;
+    if (grid > sms) grid = sms;
+    vadv_pipeline_kernel<<<(unsigned)grid, VA_THREADS, bytes, npb::st().stream>>>(p);
+    NPB_CHECK_LAUNCH("vadv_pipeline_kernel");
     npb::count_launch();
     return 0;
 }
