@@ -84,6 +84,7 @@ struct ResidentParams {
     double *A, *B;
     unsigned long long *inbox;   // [PI*PJ][HR_SLOTS][4 sides][face_rows][n2-2]
     int fences;                  // 1: periodic gpu-scope fences (formal release/acquire chain)
+    int max_bcells;              // capacity of the rim-cell table (entries)
     unsigned backoff_ns;
 };
 
@@ -169,6 +170,44 @@ heat3d_resident_kernel(ResidentParams p) {
         }
     }
 
+    // cell tables (sweep invariant), placed after the two state buffers in shared memory
+    int4 *btab = reinterpret_cast<int4 *>(sm + 2 * bufsz);
+    const int n_b_rows = nit * njt - max(nit - 2, 0) * max(njt - 2, 0);      // rows (ii,jj) on the tile's rim
+    const int n_bcells = n_b_rows * nk;
+    const int n_icells = (nit * njt - n_b_rows) * nk;
+    int2 *itab = reinterpret_cast<int2 *>(btab + p.max_bcells);
+    for (int w = tid; w < nit * njt * nk; w += HR_THREADS) {
+        const int r = w / nk, kk = w - r * nk;
+        const int ii = r / njt, jj = r - ii * njt;
+        const bool rim = (ii == 0 || ii == nit - 1 || jj == 0 || jj == njt - 1);
+        // rank of this row among rim / interior rows, in row-major order
+        int rank;
+        if (rim) {
+            if (ii == 0) rank = jj;
+            else if (ii == nit - 1) rank = n_b_rows - njt + jj;
+            else rank = njt + 2 * (ii - 1) + (jj == 0 ? 0 : 1);
+            if (njt == 1 && ii > 0 && ii < nit - 1) rank = njt + (ii - 1);    // single-column tiles: one rim row per plane
+        } else {
+            rank = (ii - 1) * (njt - 2) + (jj - 1);
+        }
+        const int soff = (ii + 1) * ps + (jj + 1) * rs + 1 + kk;
+        const int goff = (int)((long long)(ilo + ii) * gps + (long long)(jlo + jj) * grs + 1 + kk);
+        if (rim) {
+            int box[2] = {-1, -1};
+            int nb = 0;
+            // my face towards side X lands in the neighbour's opposite side
+            if (ii == 0 && has_nb[0]) box[nb++] = (int)((size_t)nb_id[0] * box_sz + 1 * side_sz + (size_t)jj * nk + kk);
+            if (ii == nit - 1 && has_nb[1]) box[nb++] = (int)((size_t)nb_id[1] * box_sz + 0 * side_sz + (size_t)jj * nk + kk);
+            // (a tile is only 1 wide along an axis that is not partitioned, so nb never exceeds 2)
+            if (jj == 0 && has_nb[2] && nb < 2) box[nb++] = (int)((size_t)nb_id[2] * box_sz + 3 * side_sz + (size_t)ii * nk + kk);
+            if (jj == njt - 1 && has_nb[3] && nb < 2) box[nb++] = (int)((size_t)nb_id[3] * box_sz + 2 * side_sz + (size_t)ii * nk + kk);
+            btab[rank * nk + kk] = make_int4(soff, goff, box[0], box[1]);
+        } else {
+            itab[rank * nk + kk] = make_int2(soff, goff);
+        }
+    }
+    __syncthreads();
+
     for (int s = 1; s <= p.nsweeps; ++s) {
         double *cur = (s & 1) ? buf0 : buf1;          // state s-1
         double *nxt = (s & 1) ? buf1 : buf0;          // state s
@@ -203,41 +242,40 @@ heat3d_resident_kernel(ResidentParams p) {
         // (barrier) -> fence -> my data -> neighbour's read -> neighbour's fence -> its rewrite
         // is a happens-before chain as long as 2*HR_FENCE_EVERY <= HR_SLOTS.
         if (p.fences && (s % HR_FENCE_EVERY) == 0) __threadfence();
-        // ---- update: one (jj, k) column per thread, marching along ii; face cells also go to the
-        //      neighbours' inboxes (not after the last sweep: nobody would consume them)
+        // ---- update.  Pass 1: the boundary cells of the tile (faces towards the four neighbours),
+        //      each stored to shared memory and pushed straight into the neighbours' inboxes, so the
+        //      faces are on their way within the first fraction of the sweep.  Pass 2: the interior
+        //      cells, while the faces travel.  Cell lists are precomputed tables in shared memory.
         const bool write_all = (s >= p.nsweeps - 1);
-        const bool send = (s < p.nsweeps);
-        const size_t out_slot = (size_t)(s % HR_SLOTS) * slot_sz;
-        for (int col = tid; col < ncols; col += HR_THREADS) {
-            const int jj = col / nk, kk = col - jj * nk;
-            const double *q = cur + ps + (jj + 1) * rs + 1 + kk;        // (ii = 0, jj, k)
-            double *o = nxt + ps + (jj + 1) * rs + 1 + kk;
-            double *g = gout + (long long)ilo * gps + (long long)(jlo + jj) * grs + 1 + kk;
-            double up = q[-ps], ce = q[0];
-#pragma unroll 2
-            for (int ii = 0; ii < nit; ++ii) {
-                const double dn = q[ps];
-                const double c2 = 2.0 * ce;
-                const double t1 = 0.125 * ((dn - c2) + up);
-                const double t2 = 0.125 * ((q[rs] - c2) + q[-rs]);
-                const double t3 = 0.125 * ((q[1] - c2) + q[-1]);
-                const double v = ((t1 + t2) + t3) + ce;
-                *o = v;
-                if (write_all) *g = v;
-                if (send) {
-                    // my face towards side X lands in the neighbour's opposite side
-                    if (ii == 0 && has_nb[0])
-                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[0] * box_sz + out_slot + 1 * side_sz + (size_t)jj * nk + kk), v);
-                    if (ii == nit - 1 && has_nb[1])
-                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[1] * box_sz + out_slot + 0 * side_sz + (size_t)jj * nk + kk), v);
-                    if (jj == 0 && has_nb[2])
-                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[2] * box_sz + out_slot + 3 * side_sz + (size_t)ii * nk + kk), v);
-                    if (jj == njt - 1 && has_nb[3])
-                        st_relaxed_f64((double *)(p.inbox + (size_t)nb_id[3] * box_sz + out_slot + 2 * side_sz + (size_t)ii * nk + kk), v);
-                }
-                up = ce; ce = dn;
-                q += ps; o += ps; g += gps;
+        const bool send = (s < p.nsweeps);               // nobody consumes faces of the last state
+        unsigned long long *out_base = p.inbox + (size_t)(s % HR_SLOTS) * slot_sz;
+        for (int w = tid; w < n_bcells; w += HR_THREADS) {
+            const int4 e = btab[w];                      // x: shared offset, y: global offset, z/w: inbox cells or -1
+            const double *c = cur + e.x;
+            const double ce = c[0];
+            const double c2 = 2.0 * ce;
+            const double t1 = 0.125 * ((c[ps] - c2) + c[-ps]);
+            const double t2 = 0.125 * ((c[rs] - c2) + c[-rs]);
+            const double t3 = 0.125 * ((c[1] - c2) + c[-1]);
+            const double v = ((t1 + t2) + t3) + ce;
+            nxt[e.x] = v;
+            if (send) {
+                if (e.z >= 0) st_relaxed_f64((double *)(out_base + e.z), v);
+                if (e.w >= 0) st_relaxed_f64((double *)(out_base + e.w), v);
             }
+            if (write_all) gout[e.y] = v;
+        }
+        for (int w = tid; w < n_icells; w += HR_THREADS) {
+            const int2 e = itab[w];                      // x: shared offset, y: global offset
+            const double *c = cur + e.x;
+            const double ce = c[0];
+            const double c2 = 2.0 * ce;
+            const double t1 = 0.125 * ((c[ps] - c2) + c[-ps]);
+            const double t2 = 0.125 * ((c[rs] - c2) + c[-rs]);
+            const double t3 = 0.125 * ((c[1] - c2) + c[-1]);
+            const double v = ((t1 + t2) + t3) + ce;
+            nxt[e.x] = v;
+            if (write_all) gout[e.y] = v;
         }
         // the barrier at the top of the next sweep (after its receive phase) separates this
         // update from the next one; receive only touches halo cells, which no update writes
@@ -256,9 +294,10 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
     int PI = 1, PJ = 1;
     {
         long best = -1;
-        for (int a = 1; a <= in0 && a <= sms; ++a) {
+        const int a_max = in0 >= 2 ? in0 / 2 : 1, b_max = in1 >= 2 ? in1 / 2 : 1;   // partitioned axes: tiles >= 2 wide
+        for (int a = 1; a <= a_max && a <= sms; ++a) {
             int b = sms / a;
-            if (b > in1) b = in1;
+            if (b > b_max) b = b_max;
             if (b < 1) continue;
             const int ta = (in0 + a - 1) / a, tb = (in1 + b - 1) / b;
             const long cost = (long)ta * tb + 2L * (ta + tb);   // update work + halo traffic, in columns
@@ -266,8 +305,12 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
         }
     }
     const int ti_max = (in0 + PI - 1) / PI, tj_max = (in1 + PJ - 1) / PJ;
-    const size_t smem = (size_t)2 * (ti_max + 2) * (tj_max + 2) * n2 * sizeof(double);
-    if (smem + 2048 > npb::st().smem_optin) return 0;
+    const int nk = (int)n2 - 2;
+    const int max_b = (ti_max * tj_max - (ti_max > 2 ? ti_max - 2 : 0) * (tj_max > 2 ? tj_max - 2 : 0)) * nk;
+    const int max_i = (ti_max > 2 ? ti_max - 2 : 0) * (tj_max > 2 ? tj_max - 2 : 0) * nk;
+    const size_t smem = (size_t)2 * (ti_max + 2) * (tj_max + 2) * n2 * sizeof(double) + (size_t)max_b * 16 +
+                        (size_t)max_i * 8;
+    if (smem + 2048 > npb::st().smem_optin || n0 * n1 * n2 >= (1LL << 31)) return 0;
     if ((2 * ti_max + 2 * tj_max) * (n2 - 2) > HR_THREADS * HR_RECV) return 0;   // halo cells per CTA
     static size_t configured = 0;
     if (smem > configured) {
@@ -286,7 +329,7 @@ int try_resident(int64_t nsweeps, int64_t n0, int64_t n1, int64_t n2, double *A,
     unsigned long long *inbox = (unsigned long long *)npb::workspace(1, box * PI * PJ * sizeof(unsigned long long));
     if (!inbox) return 0;
     ResidentParams rp{(int)n0, (int)n1, (int)n2, PI, PJ, ti_max, tj_max, face_rows, (int)nsweeps, A, B, inbox,
-                      g_resident_fences, g_backoff_ns};
+                      g_resident_fences, max_b, g_backoff_ns};
     void *args[] = {&rp};
     cudaError_t e = cudaLaunchCooperativeKernel((void *)heat3d_resident_kernel, dim3(PI * PJ), dim3(HR_THREADS),
                                                 args, smem, npb::st().stream);
