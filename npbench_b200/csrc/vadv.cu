@@ -301,6 +301,219 @@ vadv_pipeline_kernel(VadvParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// TMA-fed variant (even K, opt-in via npb_vadv_set_mode(2)): same tiles, same solvers, but phase A no longer
+// issues global loads from the mover warps.  Measured on the kernel above
+// (tools/vadv_trace.py): (1) per-SM LDG traffic saturates at ~33 GB/s (outstanding
+// L1 miss lines), which makes the movers the bottleneck; (2) a solve takes 12-13 us
+// when its SM sub-partition is otherwise idle but ~21 us when mover warps share
+// it.  So here one producer thread streams the raw inputs of CS columns at a
+// time into a double-buffered staging area with cp.async.bulk (TMA), the three
+// solver warps sit alone on sub-partitions 1..3, and the seven mover warps --
+// all on sub-partition 0 -- only do shared-memory work: staging -> (a_k, dcol_k)
+// -> tile, and tile -> utens_stage.
+// ---------------------------------------------------------------------------
+constexpr int VT_CS = 4;                     // columns per staging chunk
+constexpr int VT_STAGES = 2;
+constexpr int VT_MOVERS = 7;                 // warps 0,4,...,24 (sub-partition 0)
+constexpr int VT_WARPS = 32;                 // warp 28 = producer; warps 1,2,3 = solvers; others exit
+constexpr int VT_PRODUCER = 4 * VT_MOVERS;
+constexpr int VT_THREADS = 32 * VT_WARPS;
+constexpr int VT_DU = 4;                     // phase-D items per batch
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// phase A from staging: chunk of `ccols` columns starting at group-local column c0
+__device__ __forceinline__ void phase_a_staged(const VadvParams &p, const double *stg, double *tA, double *tD,
+                                               int c0, int ccols, int mover, int lane) {
+    const int K = p.K, NCP = p.NCP;
+    const double dtr = p.dtr;
+    const int nkb = (K + 31) >> 5;
+    const int cstride = VT_CS * K;               // doubles per array in a stage
+    const double *s_uo = stg, *s_us = stg + cstride, *s_w0 = stg + 2 * cstride, *s_w1 = stg + 3 * cstride,
+                 *s_up = stg + 4 * cstride, *s_ut = stg + 5 * cstride;
+    for (int it = mover; it < ccols * nkb; it += VT_MOVERS) {
+        const int cl = it / nkb;
+        const int k = ((it - cl * nkb) << 5) + lane;
+        if (k >= K) continue;
+        const int km = max(k - 1, 0), kp = min(k + 1, K - 1);
+        const int o = cl * K;
+        const double u_c = s_us[o + k];
+        const double wc = s_w1[o + k] + s_w0[o + k];          // wcon[i+1,j,k] + wcon[i,j,k]
+        const double wn = s_w1[o + kp] + s_w0[o + kp];
+        const double d0 = (dtr * s_up[o + k] + s_ut[o + k]) + s_uo[o + k];
+        const double a = (-0.25 * wc) * 0.5;
+        const double cs = (0.25 * wn) * 0.5;
+        const double t_lo = (-a) * (s_us[o + km] - u_c);
+        const double t_hi = cs * (s_us[o + kp] - u_c);
+        const double corr = (k == 0) ? -t_hi : ((k < K - 1) ? (t_lo - t_hi) : t_lo);
+        tA[k * NCP + c0 + cl] = a;
+        tD[k * NCP + c0 + cl] = d0 + corr;
+    }
+}
+
+__device__ __forceinline__ void phase_d4(const VadvParams &p, const double *tD, long long col0, int nc, int mover,
+                                         int lane) {
+    const int K = p.K, NCP = p.NCP;
+    const double dtr = p.dtr;
+    const int nkb = (K + 31) >> 5;
+    const int items = nc * nkb;
+    for (int it0 = mover; it0 < items; it0 += VT_MOVERS * VT_DU) {
+        double r_up[VT_DU];
+#pragma unroll
+        for (int u = 0; u < VT_DU; ++u) {
+            const int it = min(it0 + u * VT_MOVERS, items - 1);
+            const int cc = it / nkb;
+            const int k = min(((it - cc * nkb) << 5) + lane, K - 1);
+            r_up[u] = __ldg(p.u_pos + (col0 + cc) * K + k);
+        }
+#pragma unroll
+        for (int u = 0; u < VT_DU; ++u) {
+            const int it = it0 + u * VT_MOVERS;
+            const int cc = min(it, items - 1) / nkb;
+            const int k = ((it - cc * nkb) << 5) + lane;
+            if (it < items && k < K)
+                stg_stream(p.utens_stage + (col0 + cc) * K + k, dtr * (tD[k * NCP + cc] - r_up[u]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VT_THREADS, 1)
+vadv_tma_kernel(VadvParams p) {
+    extern __shared__ __align__(128) double smem_all[];
+    __shared__ __align__(8) unsigned long long loaded[VA_TILES], solved[VA_TILES], full_bar[VT_STAGES],
+        empty_bar[VT_STAGES];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int K = p.K;
+    const size_t stage_sz = (size_t)6 * VT_CS * K;            // doubles per stage
+    double *stages = smem_all;
+    double *tiles = smem_all + VT_STAGES * stage_sz;
+    const size_t tile_sz = (size_t)2 * K * p.NCP;
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < VA_TILES; ++t) { mbar_init(&loaded[t], VT_MOVERS); mbar_init(&solved[t], 1); }
+        for (int s = 0; s < VT_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], VT_MOVERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long stride = (long long)p.ntiles * gridDim.x;
+    const long long first = (long long)blockIdx.x * p.ntiles;
+    const long long JK = (long long)p.J * K;
+
+    if (warp >= 1 && warp <= 3) {
+        // ------------------------------- solver of tile `warp - 1` (alone on its sub-partition)
+        const int t = warp - 1;
+        if (t >= p.ntiles) return;
+        double *tA = tiles + t * tile_sz, *tD = tA + (size_t)K * p.NCP;
+        unsigned n = 0;
+        for (long long g = first + t; g < p.ngroups; g += stride, ++n) {
+            const int nc = (int)min((long long)p.NC, p.ncols - g * p.NC);
+            mbar_wait(&loaded[t], n & 1u, 64);
+            stamp(p, g, 2, lane == 0);
+            phase_bc(p, tA, tD, nc, lane);
+            __syncwarp();
+            stamp(p, g, 3, lane == 0);
+            if (lane == 0) mbar_arrive(&solved[t]);
+        }
+        return;
+    }
+
+    // The A-jobs are visited in the same order by the producer and by the movers:
+    //   prologue: (tile t, group first+t) for t = 0..ntiles-1;
+    //   then for n = 0,1,..: for t: if group g(t,n) exists and g(t,n+1) exists -> A-job (t, g(t,n+1)).
+    if (warp == VT_PRODUCER) {
+        // ------------------------------- producer: one thread streams chunks with TMA
+        if (lane != 0) return;
+        unsigned job = 0;
+        auto feed = [&](long long g) {
+            const int nc = (int)min((long long)p.NC, p.ncols - g * p.NC);
+            for (int c0 = 0; c0 < nc; c0 += VT_CS, ++job) {
+                const int cc = min(VT_CS, nc - c0);
+                const int st = job % VT_STAGES;
+                mbar_wait(&empty_bar[st], ((job / VT_STAGES) & 1u) ^ 1u, 32);
+                const unsigned bytes = (unsigned)(cc * K) * 8u;
+                double *dst = stages + st * stage_sz;
+                const long long base = (g * p.NC + c0) * K;
+                mbar_arrive_expect_tx(&full_bar[st], 6u * bytes);
+                bulk_g2s(dst + 0 * VT_CS * K, p.utens_stage + base, bytes, &full_bar[st]);
+                bulk_g2s(dst + 1 * VT_CS * K, p.u_stage + base, bytes, &full_bar[st]);
+                bulk_g2s(dst + 2 * VT_CS * K, p.wcon + base, bytes, &full_bar[st]);
+                bulk_g2s(dst + 3 * VT_CS * K, p.wcon + base + JK, bytes, &full_bar[st]);
+                bulk_g2s(dst + 4 * VT_CS * K, p.u_pos + base, bytes, &full_bar[st]);
+                bulk_g2s(dst + 5 * VT_CS * K, p.utens + base, bytes, &full_bar[st]);
+            }
+        };
+        for (int t = 0; t < p.ntiles; ++t)
+            if (first + t < p.ngroups) feed(first + t);
+        for (unsigned n = 0;; ++n) {
+            bool any = false;
+            for (int t = 0; t < p.ntiles; ++t) {
+                const long long g = first + t + (long long)n * stride;
+                if (g >= p.ngroups) continue;
+                any = true;
+                if (g + stride < p.ngroups) feed(g + stride);
+            }
+            if (!any) break;
+        }
+        return;
+    }
+    if ((warp & 3) != 0 || warp >= VT_PRODUCER) return;       // warps without a role
+
+    // ----------------------------------- movers (warps 0,4,..: sub-partition 0) ------
+    const int mover = warp >> 2;
+    unsigned job = 0;
+    auto load_tile = [&](int t, long long g) {
+        double *tA = tiles + t * tile_sz, *tD = tA + (size_t)K * p.NCP;
+        const int nc = (int)min((long long)p.NC, p.ncols - g * p.NC);
+        stamp(p, g, 0, mover == 0 && lane == 0);
+        for (int c0 = 0; c0 < nc; c0 += VT_CS, ++job) {
+            const int st = job % VT_STAGES;
+            mbar_wait(&full_bar[st], (job / VT_STAGES) & 1u, 32);
+            phase_a_staged(p, stages + st * stage_sz, tA, tD, c0, min(VT_CS, nc - c0), mover, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+        stamp(p, g, 1, mover == 0 && lane == 0);
+        if (lane == 0) mbar_arrive(&loaded[t]);
+    };
+    for (int t = 0; t < p.ntiles; ++t)
+        if (first + t < p.ngroups) load_tile(t, first + t);
+    for (unsigned n = 0;; ++n) {
+        bool any = false;
+        for (int t = 0; t < p.ntiles; ++t) {
+            const long long g = first + t + (long long)n * stride;
+            if (g >= p.ngroups) continue;
+            any = true;
+            const double *tD = tiles + t * tile_sz + (size_t)K * p.NCP;
+            mbar_wait(&solved[t], n & 1u, 128);
+            stamp(p, g, 4, mover == 0 && lane == 0);
+            phase_d4(p, tD, g * p.NC, (int)min((long long)p.NC, p.ncols - g * p.NC), mover, lane);
+            stamp(p, g, 5, mover == 0 && lane == 0);
+            if (g + stride < p.ngroups) load_tile(t, g + stride);
+        }
+        if (!any) break;
+    }
+}
+
+// Geometry of the TMA variant: 3 tiles + 2 staging buffers; false if the groups would be too narrow.
+bool pick_geometry_tma(int K, size_t smem_per_block, int *NC, int *NCP, size_t *bytes) {
+    if (K & 1) return false;                                  // bulk copies need 16-byte aligned columns
+    const size_t staging = (size_t)VT_STAGES * 6 * VT_CS * K * sizeof(double);
+    for (int nc = 31; nc >= 12; --nc) {
+        if ((nc & 1) == 0) continue;                          // odd width: no padding column wasted
+        const size_t b = staging + (size_t)VA_TILES * 2 * K * nc * sizeof(double);
+        if (b + 512 <= smem_per_block) { *NC = nc; *NCP = nc; *bytes = b; return true; }
+    }
+    return false;
+}
+
 // Geometry: as many tiles (<= 3) as possible with the widest column groups that fit.
 bool pick_geometry(int K, size_t smem_per_block, int *ntiles, int *NC, int *NCP, size_t *bytes) {
     for (int nt = VA_TILES; nt >= 1; --nt)
@@ -313,10 +526,16 @@ bool pick_geometry(int K, size_t smem_per_block, int *ntiles, int *NC, int *NCP,
 }
 
 unsigned long long *g_trace = nullptr;
+int g_vadv_mode = 0;     // 0/1 LDG pipeline kernel (default), 2 TMA-fed kernel when legal
+int g_vadv_last = 0;     // 1 LDG pipeline kernel, 2 TMA-fed kernel
 
 }  // namespace
 
 // profiling aid: device buffer of ngroups*8 u64 receiving per-group phase timestamps (NULL = off)
+// 0/1: LDG pipeline kernel (default, fastest measured); 2: TMA-fed kernel for even K with enough columns
+// (solves run undisturbed at 13 us instead of 21 us, but the staged phase A is slower: 309 vs 220 us at `paper`)
+extern "C" int npb_vadv_set_mode(int mode) { g_vadv_mode = mode; return 0; }
+extern "C" int npb_vadv_last_path(void) { return g_vadv_last; }
 extern "C" int npb_vadv_set_trace(void *dev_buf) { g_trace = (unsigned long long *)dev_buf; return 0; }
 
 extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage,
@@ -329,12 +548,22 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     NPB_ARG(K < (1 << 20), "npb_vadv_f64", "K too large");
     int ntiles = 0, NC = 0, NCP = 0;
     size_t bytes = 0;
+    const int sms_ = npb::st().sm_count;
+    bool use_tma = (g_vadv_mode == 2) && pick_geometry_tma((int)K, npb::st().smem_optin, &NC, &NCP, &bytes) &&
+                   (I * J + NC - 1) / NC >= (long long)VA_TILES * sms_;       // enough groups for 3 tiles per SM
+    if (use_tma) ntiles = VA_TILES;
+    else
     NPB_ARG(pick_geometry((int)K, npb::st().smem_optin, &ntiles, &NC, &NCP, &bytes), "npb_vadv_f64",
             "K too large for the shared-memory column tile");
-    static size_t configured = 0;
-    if (bytes > configured) {
+    g_vadv_last = use_tma ? 2 : 1;
+    static size_t configured = 0, configured_tma = 0;
+    if (!use_tma && bytes > configured) {
         NPB_CUDA(cudaFuncSetAttribute(vadv_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
+    }
+    if (use_tma && bytes > configured_tma) {
+        NPB_CUDA(cudaFuncSetAttribute(vadv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured_tma = bytes;
     }
     VadvParams p;
     p.ncols = I * J; p.K = (int)K; p.J = (int)J; p.NC = NC; p.NCP = NCP; p.dtr = dtr_stage;
@@ -348,8 +577,9 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     p.trace = g_trace;
     long long grid = (p.ngroups + ntiles - 1) / ntiles;
     if (grid > sms) grid = sms;
-    vadv_pipeline_kernel<<<(unsigned)grid, VA_THREADS, bytes, npb::st().stream>>>(p);
-    NPB_CHECK_LAUNCH("vadv_pipeline_kernel");
+    if (use_tma) vadv_tma_kernel<<<(unsigned)grid, VT_THREADS, bytes, npb::st().stream>>>(p);
+    else vadv_pipeline_kernel<<<(unsigned)grid, VA_THREADS, bytes, npb::st().stream>>>(p);
+    NPB_CHECK_LAUNCH("vadv kernel");
     npb::count_launch();
     return 0;
 }
