@@ -31,6 +31,22 @@ void *workspace(int slot, size_t bytes);
 
 inline void count_launch(int n = 1) { st().launches += (uint64_t)n; }
 
+// ---- CUDA-graph cache for launch-bound time loops (runtime.cu) --------------------
+// A time loop of hundreds of tiny dependent launches is bound by launch cost.  The entry
+// points capture their launch sequence once per (kernel family, extents, step count,
+// device pointers) and replay it with one cudaGraphLaunch afterwards.
+struct GraphKey {
+    int kind;
+    long long dims[4];
+    const void *ptrs[7];
+};
+// true: a cached graph for `key` was launched (nothing else to do)
+bool graph_replay(const GraphKey &key);
+// begin capturing the current stream; false if capture is not possible (then launch directly)
+bool graph_begin();
+// end capture, instantiate, cache under `key` and launch once; returns 0 or a CUDA error code
+int graph_end_and_launch(const GraphKey &key);
+
 }  // namespace npb
 
 #define NPB_REQUIRE_INIT()                                                        \

@@ -102,17 +102,30 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
     NPB_ARG(ws != nullptr, "npb_fdtd2d_f64", "cannot allocate the ping-pong workspace");
     double *u[3] = {ex, ey, hz};
     double *w[3] = {ws, ws + cells, ws + 2 * cells};
-    for (int64_t t = 0; t < tmax; ++t) {
+    // TMAX short dependent launches: capture once per (extents, pointers), replay as one graph
+    npb::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.kind = 2; key.dims[0] = tmax; key.dims[1] = nx; key.dims[2] = ny;
+    key.ptrs[0] = ex; key.ptrs[1] = ey; key.ptrs[2] = hz; key.ptrs[3] = fict; key.ptrs[4] = ws;
+    const bool use_graph = tmax > 8;
+    if (use_graph && npb::graph_replay(key)) return 0;
+    const bool capturing = use_graph && npb::graph_begin();
+    int rc = 0;
+    for (int64_t t = 0; t < tmax && !rc; ++t) {
         double **s = (t & 1) ? w : u;
         double **d = (t & 1) ? u : w;
         FdtdParams p{nx, 0, nx, ny, 0, nx, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
-        const int rc = launch_step(p);
-        if (rc) return rc;
+        rc = launch_step(p);
     }
-    if (tmax & 1) {   // result lives in the workspace: bring it home
-        for (int f = 0; f < 3; ++f)
-            NPB_CUDA(cudaMemcpyAsync(u[f], w[f], cells * sizeof(double), cudaMemcpyDeviceToDevice,
-                                     npb::st().stream));
+    if (!rc && (tmax & 1)) {   // result lives in the workspace: bring it home
+        for (int f = 0; f < 3 && !rc; ++f)
+            if (cudaMemcpyAsync(u[f], w[f], cells * sizeof(double), cudaMemcpyDeviceToDevice, npb::st().stream) !=
+                cudaSuccess)
+                rc = npb::fail_cuda("fdtd2d copy-back", cudaGetLastError());
     }
-    return 0;
+    if (capturing) {
+        const int rc2 = npb::graph_end_and_launch(key);
+        if (!rc) rc = rc2;
+    }
+    return rc;
 }

@@ -540,6 +540,7 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     return 0;
 }
 
+bool g_use_graphs = true;
 int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 resident if eligible, 3 temporally blocked passes
 int g_last_path = 0;   // 1 resident persistent kernel, 2 one launch per sweep, 3 temporally blocked passes
 
@@ -550,7 +551,8 @@ int g_last_path = 0;   // 1 resident persistent kernel, 2 one launch per sweep, 
 extern "C" int npb_heat3d_set_mode(int mode) {
     g_resident_fences = (mode & 16) ? 0 : 1;
     g_backoff_ns = (mode & 32) ? 50 : ((mode & 64) ? 800 : 200);   // +16: resident kernel without the per-sweep fences (experiments)
-    g_mode = mode & 15;
+    g_mode = mode & 7;
+    g_use_graphs = !(mode & 8);                 // +8: plain launches instead of a captured graph
     return 0;
 }
 // variant used by the last npb_heat3d_f64 call: 1 resident, 2 streaming, 3 temporally blocked
@@ -584,11 +586,22 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
         if (T > 0) { g_last_path = 3; return run_tb(T, smem, 2 * (tsteps - 1), n0, n1, n2, A, B); }
     }
     g_last_path = 2;
-    for (int64_t t = 1; t < tsteps; ++t) {   // heat_3d_numpy.py:6
-        int rc = launch_sweep(n0, n1, n2, A, B, 1, n0 - 1);
-        if (rc) return rc;
-        rc = launch_sweep(n0, n1, n2, B, A, 1, n0 - 1);
-        if (rc) return rc;
+    // hundreds of short dependent launches: capture once, replay as one graph launch
+    npb::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.kind = 1; key.dims[0] = tsteps; key.dims[1] = n0; key.dims[2] = n1; key.dims[3] = n2;
+    key.ptrs[0] = A; key.ptrs[1] = B;
+    const bool use_graph = (tsteps > 8) && g_use_graphs;
+    if (use_graph && npb::graph_replay(key)) return 0;
+    const bool capturing = use_graph && npb::graph_begin();
+    int rc = 0;
+    for (int64_t t = 1; t < tsteps && !rc; ++t) {   // heat_3d_numpy.py:6
+        rc = launch_sweep(n0, n1, n2, A, B, 1, n0 - 1);
+        if (!rc) rc = launch_sweep(n0, n1, n2, B, A, 1, n0 - 1);
     }
-    return 0;
+    if (capturing) {
+        const int rc2 = npb::graph_end_and_launch(key);
+        if (!rc) rc = rc2;
+    }
+    return rc;
 }

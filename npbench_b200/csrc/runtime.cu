@@ -55,6 +55,61 @@ void *workspace(int slot, size_t bytes) {
     return w.p;
 }
 
+// ---- CUDA-graph cache ------------------------------------------------------
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches = 0;     // kernels inside the graph (for npb_launch_count)
+    uint64_t stamp = 0;        // LRU
+};
+static GraphEntry g_graphs[8];
+static uint64_t g_graph_clock = 0;
+static uint64_t g_capture_launch_base = 0;
+
+static bool same_key(const GraphKey &a, const GraphKey &b) { return memcmp(&a, &b, sizeof(GraphKey)) == 0; }
+
+bool graph_replay(const GraphKey &key) {
+    for (auto &e : g_graphs)
+        if (e.exec && same_key(e.key, key)) {
+            if (cudaGraphLaunch(e.exec, st().stream) != cudaSuccess) { cudaGetLastError(); return false; }
+            e.stamp = ++g_graph_clock;
+            st().launches += e.launches;
+            return true;
+        }
+    return false;
+}
+
+bool graph_begin() {
+    if (st().stream == nullptr) return false;                       // legacy default stream cannot be captured
+    if (cudaStreamBeginCapture(st().stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    g_capture_launch_base = st().launches;
+    return true;
+}
+
+int graph_end_and_launch(const GraphKey &key) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st().stream, &graph);
+    if (e != cudaSuccess || !graph) return fail_cuda("cudaStreamEndCapture", e == cudaSuccess ? cudaErrorUnknown : e);
+    GraphEntry *slot = &g_graphs[0];
+    for (auto &g : g_graphs) {
+        if (!g.exec) { slot = &g; break; }
+        if (g.stamp < slot->stamp) slot = &g;
+    }
+    if (slot->exec) { cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+    e = cudaGraphInstantiate(&slot->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { slot->exec = nullptr; return fail_cuda("cudaGraphInstantiate", e); }
+    slot->key = key;
+    slot->launches = st().launches - g_capture_launch_base;          // counted while capturing
+    slot->stamp = ++g_graph_clock;
+    e = cudaGraphLaunch(slot->exec, st().stream);
+    if (e != cudaSuccess) return fail_cuda("cudaGraphLaunch", e);
+    return 0;
+}
+
 }  // namespace npb
 
 using namespace npb;
@@ -97,6 +152,7 @@ int npb_shutdown(void) {
     cudaDeviceSynchronize();
     npb_pool_trim();
     for (auto &w : g_ws) { if (w.p) cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+    for (auto &g : g_graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     cudaEventDestroy(s.ev0); cudaEventDestroy(s.ev1);
     cudaStreamDestroy(s.own_stream);
     s = State();
