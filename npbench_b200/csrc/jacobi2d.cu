@@ -22,50 +22,59 @@
 namespace {
 
 constexpr int JB_HP = 8;                       // halo padding (even, >= max nsteps)
-constexpr int JB_C = 128;                      // shared tile columns
-constexpr int JB_TJ = JB_C - 2 * JB_HP;        // 112 output columns per tile
-constexpr int JB_TI = 32;                      // output rows per tile
-constexpr int JB_R = JB_TI + 2 * NPB_JACOBI2D_MAX_BLOCK;   // 46 shared tile rows
 constexpr int JB_THREADS = 256;
-constexpr int JB_SEGS = JB_THREADS / (JB_C / 2);           // 4 row segments
-constexpr int JB_LD = (JB_R * JB_C) / JB_THREADS;          // 23 tile elements per thread
-static_assert(JB_LD * JB_THREADS == JB_R * JB_C, "tile must divide evenly over the threads");
-constexpr size_t JB_SMEM = (size_t)2 * JB_R * JB_C * sizeof(double);   // 94208 B
 
+// Tile geometry.  Big grids use the 32 x 112 tile (least halo redundancy); small grids switch
+// to smaller tiles so that every SM gets work (NPBench S/M/L are 150^2 .. 700^2).
+template <int C_, int TI_>
+struct JacobiTile {
+    static constexpr int C = C_;                          // shared tile columns
+    static constexpr int TJ = C_ - 2 * JB_HP;             // output columns per tile
+    static constexpr int TI = TI_;                        // output rows per tile
+    static constexpr int R = TI_ + 2 * NPB_JACOBI2D_MAX_BLOCK;   // shared tile rows
+    static constexpr int SEGS = JB_THREADS / (C_ / 2);    // row segments
+    static constexpr int LD = (R * C_ + JB_THREADS - 1) / JB_THREADS;   // tile elements per thread
+    static constexpr size_t SMEM = (size_t)2 * R * C_ * sizeof(double);
+};
+using TileBig = JacobiTile<128, 32>;     // 46 x 128 region, 94 KB, 2 CTAs/SM
+using TileMid = JacobiTile<128, 16>;     // 30 x 128 region, 61 KB
+using TileSmall = JacobiTile<64, 8>;     // 22 x 64 region, 22 KB
+
+template <class T>
 __global__ void __launch_bounds__(JB_THREADS, 2)
 jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__restrict__ src,
                       double *__restrict__ dst, long long tile_row0) {
     extern __shared__ __align__(16) double sm[];
     double *buf0 = sm;                 // states of src parity
-    double *buf1 = sm + JB_R * JB_C;   // states of dst parity
+    double *buf1 = sm + T::R * T::C;   // states of dst parity
     const int h = nsteps;
-    const long long i0 = 1 + (tile_row0 + blockIdx.y) * JB_TI;   // first output row
-    const long long j0 = 1 + (long long)blockIdx.x * JB_TJ;      // first output column
+    const long long i0 = 1 + (tile_row0 + blockIdx.y) * T::TI;   // first output row
+    const long long j0 = 1 + (long long)blockIdx.x * T::TJ;      // first output column
     // shared (r, c)  <->  global (i0 - MAXB + r, j0 - HP + c)
     const long long gi_base = i0 - NPB_JACOBI2D_MAX_BLOCK;
     const long long gj_base = j0 - JB_HP;
 
     // ---- load: rows [i0-h, i0+TI+h), cols [j0-h, j0+TJ+h), clipped to the grid
-    const long long r_lo = max(0LL, i0 - h), r_hi = min(ni - 1, i0 + JB_TI - 1 + h);
-    const long long c_lo = max(0LL, j0 - h), c_hi = min(nj - 1, j0 + JB_TJ - 1 + h);
-    // All JB_LD loads of a thread are issued before the first shared store, so ~23 x 8 B per
+    const long long r_lo = max(0LL, i0 - h), r_hi = min(ni - 1, i0 + T::TI - 1 + h);
+    const long long c_lo = max(0LL, j0 - h), c_hi = min(nj - 1, j0 + T::TJ - 1 + h);
+    // All T::LD loads of a thread are issued before the first shared store, so ~23 x 8 B per
     // thread are in flight (the load phase was global-latency bound when unrolled only x4).
     {
-        double v[JB_LD];
+        double v[T::LD];
 #pragma unroll
-        for (int u = 0; u < JB_LD; ++u) {
+        for (int u = 0; u < T::LD; ++u) {
             const int idx = threadIdx.x + u * JB_THREADS;
-            const int r = idx / JB_C, c = idx % JB_C;
+            const int r = idx / T::C, c = idx % T::C;
             const long long gi = gi_base + r, gj = gj_base + c;
-            const bool in = gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi;
+            const bool in = idx < T::R * T::C && gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi;
             v[u] = in ? __ldg(src + gi * nj + gj) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < JB_LD; ++u) {
+        for (int u = 0; u < T::LD; ++u) {
             const int idx = threadIdx.x + u * JB_THREADS;
-            const int r = idx / JB_C, c = idx % JB_C;
+            const int r = idx / T::C, c = idx % T::C;
             const long long gi = gi_base + r, gj = gj_base + c;
-            if (gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi) {
+            if (idx < T::R * T::C && gi >= r_lo && gi <= r_hi && gj >= c_lo && gj <= c_hi) {
                 buf0[idx] = v[u];
                 if (gi == 0 || gi == ni - 1 || gj == 0 || gj == nj - 1)
                     buf1[idx] = __ldg((const double *)dst + gi * nj + gj);   // dst's own constant border
@@ -75,30 +84,30 @@ jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__re
     __syncthreads();
 
     // ---- nsteps sweeps on a shrinking region
-    const int pair = threadIdx.x % (JB_C / 2);   // column pair: shared cols 2*pair, 2*pair+1
-    const int seg = threadIdx.x / (JB_C / 2);    // row segment
+    const int pair = threadIdx.x % (T::C / 2);   // column pair: shared cols 2*pair, 2*pair+1
+    const int seg = threadIdx.x / (T::C / 2);    // row segment
     const int cs0 = 2 * pair;
     for (int s = 1; s <= nsteps; ++s) {
         const double *in = (s & 1) ? buf0 : buf1;
         double *out = (s & 1) ? buf1 : buf0;
         // update region in global coordinates, clipped to the interior
-        const long long ui_lo = max(1LL, i0 - h + s), ui_hi = min(ni - 2, i0 + JB_TI - 1 + h - s);
-        const long long uj_lo = max(1LL, j0 - h + s), uj_hi = min(nj - 2, j0 + JB_TJ - 1 + h - s);
+        const long long ui_lo = max(1LL, i0 - h + s), ui_hi = min(ni - 2, i0 + T::TI - 1 + h - s);
+        const long long uj_lo = max(1LL, j0 - h + s), uj_hi = min(nj - 2, j0 + T::TJ - 1 + h - s);
         const int rr_lo = (int)(ui_lo - gi_base), rr_hi = (int)(ui_hi - gi_base);   // shared rows
         const int cc_lo = (int)(uj_lo - gj_base), cc_hi = (int)(uj_hi - gj_base);   // shared cols
         const int nrows = rr_hi - rr_lo + 1;
         if (nrows > 0 && cs0 + 1 >= cc_lo && cs0 <= cc_hi) {
-            const int per = (nrows + JB_SEGS - 1) / JB_SEGS;
+            const int per = (nrows + T::SEGS - 1) / T::SEGS;
             const int ra = rr_lo + seg * per;
             const int rb = min(rr_hi, ra + per - 1);
             if (ra <= rb) {
                 const bool w0 = (cs0 >= cc_lo), w1 = (cs0 + 1 <= cc_hi);
-                const double *pin = in + ra * JB_C + cs0;
-                double *pout = out + ra * JB_C + cs0;
-                double2 up = *reinterpret_cast<const double2 *>(pin - JB_C);
+                const double *pin = in + ra * T::C + cs0;
+                double *pout = out + ra * T::C + cs0;
+                double2 up = *reinterpret_cast<const double2 *>(pin - T::C);
                 double2 ce = *reinterpret_cast<const double2 *>(pin);
                 for (int r = ra; r <= rb; ++r) {
-                    const double2 dn = *reinterpret_cast<const double2 *>(pin + JB_C);
+                    const double2 dn = *reinterpret_cast<const double2 *>(pin + T::C);
                     const double left = pin[-1];
                     const double right = pin[2];
                     double2 res;
@@ -112,7 +121,7 @@ jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__re
                         pout[1] = res.y;
                     }
                     up = ce; ce = dn;
-                    pin += JB_C; pout += JB_C;
+                    pin += T::C; pout += T::C;
                 }
             }
         }
@@ -121,32 +130,33 @@ jacobi2d_block_kernel(int nsteps, long long ni, long long nj, const double *__re
 
     // ---- store the tile centre (interior cells only) from the last buffer
     const double *fin = (nsteps & 1) ? buf1 : buf0;
-    const long long o_ihi = min(ni - 2, i0 + JB_TI - 1), o_jhi = min(nj - 2, j0 + JB_TJ - 1);
-    for (int idx = threadIdx.x; idx < JB_TI * JB_TJ; idx += JB_THREADS) {
-        const int r = idx / JB_TJ, c = idx % JB_TJ;
+    const long long o_ihi = min(ni - 2, i0 + T::TI - 1), o_jhi = min(nj - 2, j0 + T::TJ - 1);
+    for (int idx = threadIdx.x; idx < T::TI * T::TJ; idx += JB_THREADS) {
+        const int r = idx / T::TJ, c = idx % T::TJ;
         const long long gi = i0 + r, gj = j0 + c;
         if (gi <= o_ihi && gj <= o_jhi)
-            dst[gi * nj + gj] = fin[(r + NPB_JACOBI2D_MAX_BLOCK) * JB_C + (c + JB_HP)];
+            dst[gi * nj + gj] = fin[(r + NPB_JACOBI2D_MAX_BLOCK) * T::C + (c + JB_HP)];
     }
 }
 
-int launch_block(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst,
-                 int64_t tr_lo, int64_t tr_hi) {
+template <class T>
+int launch_block_t(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, int64_t tr_lo,
+                   int64_t tr_hi) {
     static bool configured = false;
     if (!configured) {
-        NPB_CUDA(cudaFuncSetAttribute(jacobi2d_block_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_SMEM));
+        NPB_CUDA(cudaFuncSetAttribute(jacobi2d_block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)T::SMEM));
         configured = true;
     }
-    const int64_t tiles_i = (ni - 2 + JB_TI - 1) / JB_TI;
-    const int64_t tiles_j = (nj - 2 + JB_TJ - 1) / JB_TJ;
+    const int64_t tiles_i = (ni - 2 + T::TI - 1) / T::TI;
+    const int64_t tiles_j = (nj - 2 + T::TJ - 1) / T::TJ;
     if (tr_hi < 0 || tr_hi > tiles_i) tr_hi = tiles_i;
     if (tr_lo < 0) tr_lo = 0;
     // grid.y is limited to 65535 tile rows per launch
     for (int64_t t0 = tr_lo; t0 < tr_hi; t0 += 65535) {
         const int64_t cnt = (tr_hi - t0 < 65535) ? (tr_hi - t0) : 65535;
         dim3 grid((unsigned)tiles_j, (unsigned)cnt);
-        jacobi2d_block_kernel<<<grid, JB_THREADS, JB_SMEM, npb::st().stream>>>(
+        jacobi2d_block_kernel<T><<<grid, JB_THREADS, T::SMEM, npb::st().stream>>>(
             nsteps, (long long)ni, (long long)nj, src, dst, (long long)t0);
         NPB_CHECK_LAUNCH("jacobi2d_block_kernel");
         npb::count_launch();
@@ -154,9 +164,25 @@ int launch_block(int nsteps, int64_t ni, int64_t nj, const double *src, double *
     return 0;
 }
 
+// tile choice for whole-grid passes: the largest tile that still gives every SM ~2 CTAs
+int pick_tile(int64_t ni, int64_t nj) {
+    const int64_t want = 2LL * npb::st().sm_count;
+    auto tiles = [&](int ti, int tj) { return ((ni - 2 + ti - 1) / ti) * ((nj - 2 + tj - 1) / tj); };
+    if (tiles(TileBig::TI, TileBig::TJ) >= want) return 0;
+    if (tiles(TileMid::TI, TileMid::TJ) >= want) return 1;
+    return 2;
+}
+
+int launch_block(int tile, int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, int64_t tr_lo,
+                 int64_t tr_hi) {
+    if (tile == 0) return launch_block_t<TileBig>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+    if (tile == 1) return launch_block_t<TileMid>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+    return launch_block_t<TileSmall>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+}
+
 }  // namespace
 
-extern "C" int npb_jacobi2d_tile_rows(void) { return JB_TI; }
+extern "C" int npb_jacobi2d_tile_rows(void) { return TileBig::TI; }
 
 extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src,
                                       double *dst, int64_t tile_row_lo, int64_t tile_row_hi) {
@@ -164,9 +190,9 @@ extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const 
     NPB_ARG(nsteps >= 1 && nsteps <= NPB_JACOBI2D_MAX_BLOCK && (nsteps & 1), "npb_jacobi2d_block_f64",
             "nsteps must be odd and in 1..7");
     NPB_ARG(ni >= 0 && nj >= 0, "npb_jacobi2d_block_f64", "negative extent");
-    NPB_ARG(nj - 2 < (int64_t)JB_TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
+    NPB_ARG(nj - 2 < (int64_t)TileBig::TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
     if (ni < 3 || nj < 3) return 0;   // no interior
-    return launch_block(nsteps, ni, nj, src, dst, tile_row_lo, tile_row_hi);
+    return launch_block(0, nsteps, ni, nj, src, dst, tile_row_lo, tile_row_hi);   // the sharded driver's big tile
 }
 
 extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {
@@ -181,16 +207,30 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
     if ((n & 1) == 0) ++n;
     int64_t extra_pairs = (M - n) / 2;            // distribute in units of 2 sweeps
     const int64_t cap = (NPB_JACOBI2D_MAX_BLOCK - 1) / 2;
+    const int tile = pick_tile(ni, nj);
+    // many short dependent passes on small grids: capture once, replay as one graph launch
+    npb::GraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.kind = 3; key.dims[0] = tsteps; key.dims[1] = ni; key.dims[2] = nj;
+    key.ptrs[0] = A; key.ptrs[1] = B;
+    const bool use_graph = (n >= 8) && ni * nj <= (1LL << 24);
+    if (use_graph && npb::graph_replay(key)) return 0;
+    const bool capturing = use_graph && npb::graph_begin();
     double *src = A, *dst = B;
-    for (int64_t p = 0; p < n; ++p) {
+    int rc = 0;
+    for (int64_t p = 0; p < n && !rc; ++p) {
         const int64_t left = n - p;
         int64_t take = (extra_pairs + left - 1) / left;   // spread evenly
         if (take > cap) take = cap;
         extra_pairs -= take;
-        const int rc = launch_block((int)(1 + 2 * take), ni, nj, src, dst, 0, -1);
-        if (rc) return rc;
+        rc = launch_block(tile, (int)(1 + 2 * take), ni, nj, src, dst, 0, -1);
         double *t = src; src = dst; dst = t;
     }
     // now src == B (state S-1), dst == A
-    return launch_block(1, ni, nj, src, dst, 0, -1);
+    if (!rc) rc = launch_block(tile, 1, ni, nj, src, dst, 0, -1);
+    if (capturing) {
+        const int rc2 = npb::graph_end_and_launch(key);
+        if (!rc) rc = rc2;
+    }
+    return rc;
 }
