@@ -359,6 +359,7 @@ def multi_gpu(args, world, rank, local_rank):
     import torch
     import torch.distributed as dist
     from npbench_b200 import distributed as D
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = D.B200Engine(local_rank)
