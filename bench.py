@@ -359,7 +359,11 @@ def multi_gpu(args, world, rank, local_rank):
     import torch
     import torch.distributed as dist
     from npbench_b200 import distributed as D
-    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line only)
+    # NCCL prints its version banner on stdout at communicator creation; stdout must carry exactly
+    # one JSON line, so everything but the final print goes to stderr (fd-level redirect).
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = D.B200Engine(local_rank)
@@ -461,7 +465,10 @@ def multi_gpu(args, world, rank, local_rank):
                 "single_gpu_same_workload": {"value": round(solo_val, 3), "unit": UNIT,
                                              "note": "one slab, no halo exchange, same run; efficiency = value / (n_gpus x this)"},
                 "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dist.barrier()
     dist.destroy_process_group()
 
