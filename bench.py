@@ -355,6 +355,71 @@ def single_gpu(args):
 
 
 # ------------------------------------------------------------------ N > 1
+def multi_gpu_suite(args, world, rank, eng, D, torch, dist, peak):
+    """Other sharded kernels at N GPUs (max over ranks, CUDA events): fdtd_2d weak-scaled with halo
+    exchange; heat_3d weak-scaled with halo exchange; hdiff / vadv `paper` column-sharded (no exchange)."""
+    L = eng.lib
+    rows = []
+
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps + 1):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.median(ts[1:]))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def add(kernel, workload, units, bpu, ms):
+        gc = units / (ms * 1e-3) / 1e9
+        rows.append({"kernel": kernel, "workload": workload, "ms": round(ms, 4), "value": round(gc, 2),
+                     "frac_of_peak_per_gpu": round(gc * bpu / world / peak, 3)})
+
+    try:   # fdtd_2d: (N*8192) x 65536, TMAX = 10, ghost depth 4
+        nx, ny, tmax, H = world * 8192, 65536, 10, 4
+        slab = D.Slab(nx, world, rank, H)
+        f = [eng.empty(slab.nloc, ny) for _ in range(3)]
+        L.init_fdtd2d_f64(tmax, nx, ny, slab.row0, slab.nloc, f[0].data_ptr(), f[1].data_ptr(), f[2].data_ptr(), 0)
+        fict = [float(t) for t in range(tmax)]
+        ms = timed(lambda: D.fdtd_2d_sharded(eng, slab, tmax, f[0], f[1], f[2], fict))
+        add("fdtd_2d", "%dx%d TMAX=%d, row slabs, halo every %d steps" % (nx, ny, tmax, H), tmax * nx * ny, 48.0, ms)
+        del f
+    except Exception as e:
+        rows.append({"kernel": "fdtd_2d", "error": str(e)[:160]})
+    torch.cuda.empty_cache()
+    try:   # heat_3d: (N*512) x 1024 x 1024, TSTEPS = 6, ghost depth 4
+        n1, ts, H = 1024, 6, 4
+        n0 = world * 512
+        slab = D.Slab(n0, world, rank, H)
+        A, B = eng.empty(slab.nloc, n1, n1), eng.empty(slab.nloc, n1, n1)
+        A.uniform_(); B.copy_(A)
+        ms = timed(lambda: D.heat_3d_sharded(eng, slab, ts, A, B))
+        add("heat_3d", "%dx%dx%d TSTEPS=%d, i-plane slabs, halo every %d sweeps" % (n0, n1, n1, ts, H),
+            2 * (ts - 1) * (n0 - 2) * (n1 - 2) ** 2, 16.0, ms)
+        del A, B
+    except Exception as e:
+        rows.append({"kernel": "heat_3d", "error": str(e)[:160]})
+    torch.cuda.empty_cache()
+    try:   # hdiff / vadv `paper`, split along I (fixed overlaps, no run-time exchange)
+        I, J, K = 256, 256, 160
+        lo, hi = D.hdiff_shard(I, world, rank)
+        inf, out, cf = eng.empty(hi - lo + 4, J + 4, K).uniform_(), eng.empty(hi - lo, J, K), eng.empty(hi - lo, J, K).uniform_()
+        ms = timed(lambda: eng.hdiff(inf, out, cf), reps=10)
+        add("hdiff", "paper 256x256x160 split along I over %d GPUs, no exchange" % world, I * J * K,
+            8.0 * ((I + 4) * (J + 4) + 2 * I * J) / (I * J), ms)
+        lo, hi = D.vadv_shard(I, world, rank)
+        t = [eng.empty(hi - lo, J, K).uniform_() for _ in range(2)] + [eng.empty(hi - lo + 1, J, K).uniform_()] + \
+            [eng.empty(hi - lo, J, K).uniform_() for _ in range(2)]
+        ms = timed(lambda: eng.vadv(*t, 0.15), reps=10)
+        add("vadv", "paper 256x256x160 split along I over %d GPUs, no exchange" % world, I * J * K, 8.0 * (6 * I + 1) / I, ms)
+    except Exception as e:
+        rows.append({"kernel": "hdiff/vadv", "error": str(e)[:160]})
+    return rows
+
+
 def multi_gpu(args, world, rank, local_rank):
     import torch
     import torch.distributed as dist
@@ -443,6 +508,10 @@ def multi_gpu(args, world, rank, local_rank):
     except Exception as e:
         e2e = {"value": None, "unit": UNIT, "note": "failed: %s" % str(e)[:160]}
 
+    del A, B
+    torch.cuda.empty_cache()
+    suite = multi_gpu_suite(args, world, rank, eng, D, torch, dist, peak) if not args.no_suite else None
+
     # dominant kernel: the blocked jacobi pass (7 sweeps fused): 16 B x cells x sweeps per launch
     per_launch_sweeps = 2 * (WEAK_TSTEPS - 1) / max(1, len(D.jacobi_plan(2 * (WEAK_TSTEPS - 1))))
     achieved = value * 16.0 / world
@@ -464,7 +533,7 @@ def multi_gpu(args, world, rank, local_rank):
                                      "traffic is far below the algorithmic bytes" % per_launch_sweeps},
                 "single_gpu_same_workload": {"value": round(solo_val, 3), "unit": UNIT,
                                              "note": "one slab, no halo exchange, same run; efficiency = value / (n_gpus x this)"},
-                "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+                "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "suite": suite}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -11,5 +11,7 @@ print("%-10s %-12s %10s %10s %8s %8s" % ("kernel", "preset", "ms", "Gcell/s", "f
 for r in s:
     if "error" in r:
         print(r)
+    elif "workload" in r:
+        print("%-10s %-70s %10.4f %10.2f %8.3f" % (r["kernel"], r["workload"][:70], r["ms"], r["value"], r["frac_of_peak_per_gpu"]))
     else:
         print("%-10s %-12s %10.4f %10.2f %8.3f %8d" % (r["kernel"], r["preset"], r["ms"], r["value"], r["frac_of_peak"], r["launches"]))
