@@ -58,7 +58,7 @@ class ClockSampler:
                0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
                0x10: "sync_boost"}
 
-    def __init__(self, device_index, period=0.02):
+    def __init__(self, device_index, period=0.005):
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self.period, self._stop, self._t, self.ok = period, threading.Event(), None, False
         try:
@@ -74,21 +74,24 @@ class ClockSampler:
         except Exception as e:                                   # pragma: no cover
             self.err = repr(e)
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
-        while not self._stop.is_set():
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
             self._stop.wait(self.period)
 
     def __enter__(self):
@@ -98,6 +101,8 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.ok:
+            self._sample()            # at least one sample taken while the last timed step is still hot
         self._stop.set()
         if self._t:
             self._t.join()
