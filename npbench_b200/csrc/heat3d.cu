@@ -16,6 +16,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "inbox.cuh"
 
 namespace {
 
@@ -96,8 +97,6 @@ constexpr int HR_THREADS = 512;
 constexpr int HR_SLOTS = 12;         // inbox ring depth (sweeps)
 constexpr int HR_FENCE_EVERY = 4;    // gpu-scope fence cadence (sweeps); needs 2*cadence <= HR_SLOTS
 constexpr int HR_RECV = 4;           // inbox cells requested per thread before the first test
-constexpr unsigned long long HR_SENTINEL = 0x7FF400017FF40001ULL;   // sNaN: never an arithmetic result
-
 struct ResidentParams {
     int n0, n1, n2;          // grid extents
     int PI, PJ;              // tiles along i and j
@@ -110,23 +109,6 @@ struct ResidentParams {
     int max_bcells;              // capacity of the rim-cell table (entries)
     unsigned backoff_ns;
 };
-
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_f64(double *p, double v) {
-    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ void tile_bounds(int n_int, int parts, int t, int &lo, int &hi) {
-    const int base = n_int / parts, rem = n_int % parts;      // interior index 0 == global index 1
-    lo = 1 + t * base + min(t, rem);
-    hi = lo + base + (t < rem ? 1 : 0);
-}
 
 __global__ void __launch_bounds__(HR_THREADS, 1)
 heat3d_resident_kernel(ResidentParams p) {
