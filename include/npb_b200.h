@@ -126,8 +126,9 @@ int npb_hdiff_last_path(void);           /* 1 marching, 2 ring */
 int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
                  const double *wcon, const double *u_pos, const double *utens, double dtr_stage);
 
-int npb_vadv_set_mode(int mode);         /* 0/1 LDG pipeline kernel (default), 2 TMA-fed kernel when legal (experimental) */
-int npb_vadv_last_path(void);            /* 1 LDG pipeline kernel, 2 TMA-fed kernel */
+int npb_vadv_set_mode(int mode);         /* 0 dispatch (streaming TMEM/TMA solver for even K <= 256, else tile kernel), 1 tile kernel,
+                                            2 TMA-fed tile kernel (experimental), 3/4/5 streaming solver variants */
+int npb_vadv_last_path(void);            /* 1 tile kernel, 2 TMA-fed tile kernel, 3 streaming solver */
 int npb_vadv_set_trace(void *dev_buf);   /* profiling aid: per-group phase timestamps (ngroups*8 u64), NULL = off */
 
 /* ---- the same five calls on HOST buffers (copy in, run, copy outputs back,

@@ -526,10 +526,16 @@ bool pick_geometry(int K, size_t smem_per_block, int *ntiles, int *NC, int *NCP,
 }
 
 unsigned long long *g_trace = nullptr;
-int g_vadv_mode = 0;     // 0/1 LDG pipeline kernel (default), 2 TMA-fed kernel when legal
-int g_vadv_last = 0;     // 1 LDG pipeline kernel, 2 TMA-fed kernel
+int g_vadv_mode = 0;     // 0 dispatch (streaming solver when eligible), 1 tile kernel, 2 TMA-fed tile kernel,
+                         // 3/4/5 streaming solver variants 1/2/3 (vadv_stream.cu)
+int g_vadv_last = 0;     // 1 tile kernel, 2 TMA-fed tile kernel, 3 streaming solver
 
 }  // namespace
+
+namespace npb {
+int vadv_stream_launch(int variant, int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
+                       const double *wcon, const double *u_pos, const double *utens, double dtr);
+}
 
 // profiling aid: device buffer of ngroups*8 u64 receiving per-group phase timestamps (NULL = off)
 // 0/1: LDG pipeline kernel (default, fastest measured); 2: TMA-fed kernel for even K with enough columns
@@ -546,6 +552,12 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     NPB_ARG(K >= 2, "npb_vadv_f64", "K must be >= 2 (the reference indexes level k+1 at k=0)");
     if (I == 0 || J == 0) return 0;
     NPB_ARG(K < (1 << 20), "npb_vadv_f64", "K too large");
+    if (g_vadv_mode == 0 || g_vadv_mode >= 3) {
+        const int rc = npb::vadv_stream_launch(g_vadv_mode == 0 ? 0 : g_vadv_mode - 2, I, J, K, utens_stage, u_stage,
+                                               wcon, u_pos, utens, dtr_stage);
+        if (rc < 0) return npb::fail_cuda("vadv stream kernel", cudaGetLastError());
+        if (rc == 1) { g_vadv_last = 3; return 0; }
+    }
     int ntiles = 0, NC = 0, NCP = 0;
     size_t bytes = 0;
     const int sms_ = npb::st().sm_count;

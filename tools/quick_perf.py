@@ -39,6 +39,8 @@ def timed(fn, reps, flush=True):
 def main():
     nb.init(0)
     L = nb.lib()
+    if os.environ.get('NPB_VADV_MODE'):
+        L.vadv_set_mode(int(os.environ['NPB_VADV_MODE']))
     if os.environ.get('NPB_HEAT_MODE'):
         L.heat3d_set_mode(int(os.environ['NPB_HEAT_MODE']))
     rng = np.random.default_rng(0)
