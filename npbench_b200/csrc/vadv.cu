@@ -534,7 +534,7 @@ int g_vadv_last = 0;     // 1 tile kernel, 2 TMA-fed tile kernel, 3 streaming so
 
 namespace npb {
 int vadv_stream_launch(int variant, int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
-                       const double *wcon, const double *u_pos, const double *utens, double dtr);
+                       const double *wcon, const double *u_pos, const double *utens, double dtr, unsigned long long *trace);
 }
 
 // profiling aid: device buffer of ngroups*8 u64 receiving per-group phase timestamps (NULL = off)
@@ -554,7 +554,7 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     NPB_ARG(K < (1 << 20), "npb_vadv_f64", "K too large");
     if (g_vadv_mode == 0 || g_vadv_mode >= 3) {
         const int rc = npb::vadv_stream_launch(g_vadv_mode == 0 ? 0 : g_vadv_mode - 2, I, J, K, utens_stage, u_stage,
-                                               wcon, u_pos, utens, dtr_stage);
+                                               wcon, u_pos, utens, dtr_stage, g_trace);
         if (rc < 0) return npb::fail_cuda("vadv stream kernel", cudaGetLastError());
         if (rc == 1) { g_vadv_last = 3; return 0; }
     }
