@@ -27,6 +27,9 @@ clk = 1.965e3   # cycles per us
 print("mode %d groups %d span %.1f us" % (mode, ng, be.max()))
 print("per group: forward %.2f us (waiting for stages %.2f, of which first stage %.2f), backward %.2f us" % (
     (fe - st).mean(), (t[:, 3] / clk).mean(), (t[:, 6] / clk).mean(), (be - fe).mean()))
+n_lat = (t[:, 7] >> 32); asm_ns = t[:, 7] & 0xffffffff
+print("fills the helper had to wait for: %.1f per group, mean issue->full latency %.2f us; helper assembly %.2f us per group" % (
+    n_lat.mean(), (t[:, 4].sum() / max(n_lat.sum(), 1)) / 1e3, asm_ns.mean() / 1e3))
 print("forward quantiles us:", np.round(np.quantile(fe - st, [0, .1, .5, .9, 1]), 2))
 print("backward quantiles us:", np.round(np.quantile(be - fe, [0, .1, .5, .9, 1]), 2))
 sm = t[:, 5] >> 8
