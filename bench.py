@@ -142,6 +142,10 @@ def units_of(bench, p):
         return 2 * (p["TSTEPS"] - 1) * (p["N"] - 2) ** 3, 16.0
     if bench == "fdtd_2d":
         return p["TMAX"] * p["NX"] * p["NY"], 48.0
+    if bench == "jacobi_1d":      # widening row: one interior cell written by one sweep, read 8 + write 8
+        return 2 * (p["TSTEPS"] - 1) * (p["N"] - 2), 16.0
+    if bench == "seidel_2d":      # one interior cell updated by one Gauss-Seidel sweep (in place: read 8 + write 8)
+        return (p["TSTEPS"] - 1) * (p["N"] - 2) ** 2, 16.0
     if bench == "hdiff":
         I, J, K = p["I"], p["J"], p["K"]
         return I * J * K, 8.0 * ((I + 4) * (J + 4) + 2 * I * J) / (I * J)
@@ -163,6 +167,11 @@ SUITE = [
     ("hdiff", "L", dict(I=384, J=384, K=160)), ("hdiff", "paper", dict(I=256, J=256, K=160)),
     ("vadv", "S", dict(I=60, J=60, K=40)), ("vadv", "M", dict(I=112, J=112, K=80)),
     ("vadv", "L", dict(I=180, J=180, K=160)), ("vadv", "paper", dict(I=256, J=256, K=160)),
+    # widening row
+    ("jacobi_1d", "S", dict(TSTEPS=800, N=3200)), ("jacobi_1d", "M", dict(TSTEPS=3000, N=12000)),
+    ("jacobi_1d", "L", dict(TSTEPS=8500, N=34000)), ("jacobi_1d", "paper", dict(TSTEPS=4000, N=32000)),
+    ("seidel_2d", "S", dict(TSTEPS=8, N=50)), ("seidel_2d", "M", dict(TSTEPS=15, N=100)),
+    ("seidel_2d", "L", dict(TSTEPS=40, N=200)), ("seidel_2d", "paper", dict(TSTEPS=100, N=400)),
 ]
 
 
@@ -182,6 +191,16 @@ def make_device_case(nb, bench, p, rng):
         a = [nb.DeviceArray((p["NX"], p["NY"])) for _ in range(3)] + [nb.DeviceArray((p["TMAX"],))]
         L.init_fdtd2d_f64(p["TMAX"], p["NX"], p["NY"], 0, p["NX"], *(x.ptr for x in a))
         return a, (lambda: nb.fdtd_2d(p["TMAX"], *a))
+    if bench == "jacobi_1d":      # jacobi_1d.py:6-10
+        n = p["N"]
+        A = nb.DeviceArray.from_host((np.arange(n, dtype=np.float64) + 2.0) / n)
+        B = nb.DeviceArray.from_host((np.arange(n, dtype=np.float64) + 3.0) / n)
+        return (A, B), (lambda: nb.jacobi_1d(p["TSTEPS"], A, B))
+    if bench == "seidel_2d":      # seidel_2d.py:6-10
+        n = p["N"]
+        i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+        A = nb.DeviceArray.from_host((i * (j + 2.0) + 2.0) / n)
+        return (A,), (lambda: nb.seidel_2d(p["TSTEPS"], n, A))
     I, J, K = p["I"], p["J"], p["K"]
     if bench == "hdiff":   # hdiff.py:6-15 draws U[0,1); any U[0,1) data has the same cost
         a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]

@@ -143,6 +143,18 @@ int npb_vadv_f64_host(int64_t I, int64_t J, int64_t K, double *utens_stage, cons
                       const double *wcon, const double *u_pos, const double *utens,
                       double dtr_stage);
 
+/* ---- widening row: the next two structured-grid kernels of the suite
+ *      on the same plugin path.
+ * kernel(TSTEPS, A, B): polybench/jacobi_1d/jacobi_1d_numpy.py:4-8.  A, B of length n; end cells untouched. */
+int npb_jacobi1d_f64(int64_t tsteps, int64_t n, double *A, double *B);
+int npb_jacobi1d_f64_host(int64_t tsteps, int64_t n, double *A, double *B);
+/* kernel(TSTEPS, N, A): polybench/seidel_2d/seidel_2d_numpy.py:4-13.  A is (n, n), updated in place
+ * (Gauss-Seidel order: row by row, west to east, TSTEPS-1 sweeps). */
+int npb_seidel2d_f64(int64_t tsteps, int64_t n, double *A);
+int npb_seidel2d_f64_host(int64_t tsteps, int64_t n, double *A);
+int npb_seidel2d_set_mode(int mode);     /* 0 dispatch (distributed-shared-memory kernel when the grid fits in one cluster), 1 L2 wavefront kernel */
+int npb_seidel2d_last_path(void);        /* 1 distributed-shared-memory kernel, 2 L2 wavefront kernel */
+
 /* ---- device-side initialisers (NPBench `initialize`, closed forms):
  *      jacobi_2d.py:6-10, heat_3d.py:6-11, fdtd_2d.py:6-15.  Rows
  *      [row0, row0+nrows) of the global grid, for the scaled / sharded grids. */

@@ -97,3 +97,30 @@ extern "C" int npb_vadv_f64_host(int64_t I, int64_t J, int64_t K, double *utens_
     NPB_TRY(npb_d2h(utens_stage, d0.p, b));
     return npb_sync();
 }
+
+// ---- widening row ----------------------------------------------
+extern "C" int npb_jacobi1d_f64_host(int64_t tsteps, int64_t n, double *A, double *B) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(n >= 0, "npb_jacobi1d_f64_host", "negative extent");
+    const size_t bytes = (size_t)n * sizeof(double);
+    if (!bytes) return 0;
+    DevBuf dA, dB;
+    NPB_TRY(dA.alloc(bytes)); NPB_TRY(dB.alloc(bytes));
+    NPB_TRY(npb_h2d(dA.p, A, bytes)); NPB_TRY(npb_h2d(dB.p, B, bytes));
+    NPB_TRY(npb_jacobi1d_f64(tsteps, n, dA.d(), dB.d()));
+    NPB_TRY(npb_d2h(A, dA.p, bytes)); NPB_TRY(npb_d2h(B, dB.p, bytes));
+    return npb_sync();
+}
+
+extern "C" int npb_seidel2d_f64_host(int64_t tsteps, int64_t n, double *A) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(n >= 0, "npb_seidel2d_f64_host", "negative extent");
+    const size_t bytes = (size_t)n * (size_t)n * sizeof(double);
+    if (!bytes) return 0;
+    DevBuf dA;
+    NPB_TRY(dA.alloc(bytes));
+    NPB_TRY(npb_h2d(dA.p, A, bytes));
+    NPB_TRY(npb_seidel2d_f64(tsteps, n, dA.d()));
+    NPB_TRY(npb_d2h(A, dA.p, bytes));
+    return npb_sync();
+}

@@ -88,3 +88,23 @@ def vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage):
 def sync():
     """Block until everything enqueued on the library stream has finished."""
     _lib.lib().sync()
+
+
+# ---- widening row (SURVEY.md section 8f rank 1): bench_info/{jacobi_1d,seidel_2d}.json input_args ----
+
+def jacobi_1d(TSTEPS, A, B):
+    """kernel(TSTEPS, A, B) -- polybench/jacobi_1d/jacobi_1d_numpy.py:4-8."""
+    if A.shape != B.shape or len(A.shape) != 1:
+        raise ValueError("A and B must be 1-D arrays of the same length")
+    L = _lib.lib()
+    fn = L.jacobi1d_f64 if _kind(A, B) == "device" else L.jacobi1d_f64_host
+    fn(int(TSTEPS), A.shape[0], _p(A), _p(B))
+
+
+def seidel_2d(TSTEPS, N, A):
+    """kernel(TSTEPS, N, A) -- polybench/seidel_2d/seidel_2d_numpy.py:4-13."""
+    if len(A.shape) != 2 or A.shape[0] != A.shape[1] or A.shape[0] != int(N):
+        raise ValueError("A must be an (N, N) array")
+    L = _lib.lib()
+    fn = L.seidel2d_f64 if _kind(A) == "device" else L.seidel2d_f64_host
+    fn(int(TSTEPS), int(N), _p(A))

@@ -43,6 +43,10 @@ def lib():
         L.npb_oracle_init_jacobi2d.argtypes = [_i64, _i64, _i64, _i64, _dp, _dp]
         L.npb_oracle_init_heat3d.argtypes = [_i64, _i64, _i64, _dp, _dp]
         L.npb_oracle_init_fdtd2d.argtypes = [_i64, _i64, _i64, _i64, _i64, _dp, _dp, _dp, _dp]
+        L.npb_oracle_jacobi1d.argtypes = [_i64, _i64, _dp, _dp]
+        L.npb_oracle_init_jacobi1d.argtypes = [_i64, _dp, _dp]
+        L.npb_oracle_seidel2d.argtypes = [_i64, _i64, _dp]
+        L.npb_oracle_init_seidel2d.argtypes = [_i64, _dp]
         _LIB = L
     return _LIB
 
@@ -98,7 +102,34 @@ def vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage):
                           _ptr(utens), float(dtr_stage))
 
 
+def jacobi_1d(TSTEPS, A, B):
+    """polybench/jacobi_1d/jacobi_1d_numpy.py:4-8"""
+    assert A.ndim == 1 and B.shape == A.shape
+    lib().npb_oracle_jacobi1d(int(TSTEPS), A.shape[0], _ptr(A), _ptr(B))
+
+
+def seidel_2d(TSTEPS, N, A):
+    """polybench/seidel_2d/seidel_2d_numpy.py:4-13"""
+    assert A.shape == (N, N)
+    lib().npb_oracle_seidel2d(int(TSTEPS), int(N), _ptr(A))
+
+
 # -- initialisers (NPBench's `initialize` functions restated) ----------------
+
+def init_jacobi_1d(N):
+    """jacobi_1d.py:6-10"""
+    A = np.empty((N,)); B = np.empty((N,))
+    lib().npb_oracle_init_jacobi1d(N, _ptr(A), _ptr(B))
+    return A, B
+
+
+def init_seidel_2d(N):
+    """seidel_2d.py:6-10"""
+    A = np.empty((N, N))
+    lib().npb_oracle_init_seidel2d(N, _ptr(A))
+    return A
+
+
 
 def init_jacobi_2d(N, row0=0, nrows=None, ncols=None):
     """jacobi_2d.py:6-10; optional slab [row0, row0+nrows) x ncols of an N-row grid."""
@@ -159,4 +190,9 @@ PRESETS = {
               "L": dict(I=384, J=384, K=160), "paper": dict(I=256, J=256, K=160)},
     "vadv": {"S": dict(I=60, J=60, K=40), "M": dict(I=112, J=112, K=80),
              "L": dict(I=180, J=180, K=160), "paper": dict(I=256, J=256, K=160)},
+    # widening row: bench_info/{jacobi_1d,seidel_2d}.json:11-16
+    "jacobi_1d": {"S": dict(TSTEPS=800, N=3200), "M": dict(TSTEPS=3000, N=12000),
+                  "L": dict(TSTEPS=8500, N=34000), "paper": dict(TSTEPS=4000, N=32000)},
+    "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100),
+                  "L": dict(TSTEPS=40, N=200), "paper": dict(TSTEPS=100, N=400)},
 }

@@ -1,0 +1,74 @@
+"""Golden fixtures for the widening row: jacobi_1d and seidel_2d.
+
+    python tests/golden/make_golden_next.py            # needs /root/reference (read-only)
+
+Imports the UNMODIFIED reference
+    npbench/benchmarks/polybench/jacobi_1d/{jacobi_1d,jacobi_1d_numpy}.py
+    npbench/benchmarks/polybench/seidel_2d/{seidel_2d,seidel_2d_numpy}.py
+runs it and writes tests/golden/pins_next.json (sha256 + sum of inputs/outputs of the NPBench presets
+S and M, seidel_2d also L) and tests/golden/cases_next.npz (full arrays of small seeded cases: random
+data, odd sizes, degenerate step counts).  Kept apart from make_golden.py so that the fixtures of the
+five hot-path kernels stay byte-identical.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from make_golden import digest, ref  # noqa: E402  (also puts the reference on sys.path)
+
+PRESETS = {  # bench_info/{jacobi_1d,seidel_2d}.json "parameters"
+    "jacobi_1d": {"S": dict(TSTEPS=800, N=3200), "M": dict(TSTEPS=3000, N=12000)},
+    "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100), "L": dict(TSTEPS=40, N=200)},
+}
+
+
+def main():
+    j_init = ref("polybench/jacobi_1d", "jacobi_1d", "initialize")
+    j_kern = ref("polybench/jacobi_1d", "jacobi_1d_numpy", "kernel")
+    s_init = ref("polybench/seidel_2d", "seidel_2d", "initialize")
+    s_kern = ref("polybench/seidel_2d", "seidel_2d_numpy", "kernel")
+    pins = {"numpy": np.__version__}
+    for preset, p in PRESETS["jacobi_1d"].items():
+        A, B = j_init(p["N"])
+        e = {"in": {"A": digest(A), "B": digest(B)}}
+        j_kern(p["TSTEPS"], A, B)
+        e["out"] = {"A": digest(A), "B": digest(B)}
+        pins["jacobi_1d/" + preset] = e
+    for preset, p in PRESETS["seidel_2d"].items():
+        A = s_init(p["N"])
+        e = {"in": {"A": digest(A)}}
+        s_kern(p["TSTEPS"], p["N"], A)
+        e["out"] = {"A": digest(A)}
+        pins["seidel_2d/" + preset] = e
+    with open(os.path.join(HERE, "pins_next.json"), "w") as f:
+        json.dump(pins, f, indent=1, sort_keys=True)
+
+    cases = {}
+    rng = np.random.default_rng(20261018)
+
+    def put(name, **arrs):
+        for k, v in arrs.items():
+            cases["%s.%s" % (name, k)] = np.asarray(v)
+
+    for n, (ts, N) in enumerate([(1, 9), (2, 9), (2, 3), (3, 4), (5, 2), (40, 257), (7, 1000), (131, 700), (300, 5000),
+                                 (65, 33)]):
+        A = rng.random((N,)) - 0.5; B = rng.random((N,)) - 0.5
+        A0, B0 = A.copy(), B.copy()
+        j_kern(ts, A, B)
+        put("jacobi_1d.%d" % n, TSTEPS=ts, A_in=A0, B_in=B0, A_out=A, B_out=B)
+    for n, (ts, N) in enumerate([(1, 7), (2, 3), (2, 4), (2, 7), (3, 8), (5, 19), (9, 33), (4, 64), (12, 37), (3, 90)]):
+        A = rng.random((N, N)) - 0.5
+        A0 = A.copy()
+        s_kern(ts, N, A)
+        put("seidel_2d.%d" % n, TSTEPS=ts, N=N, A_in=A0, A_out=A)
+    np.savez_compressed(os.path.join(HERE, "cases_next.npz"), **cases)
+    print("pins:", len(pins) - 1, "cases arrays:", len(cases),
+          "npz bytes:", os.path.getsize(os.path.join(HERE, "cases_next.npz")))
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,12 @@ BENCH_INFO = {   # bench_info/<name>.json: relative_path, module_name, func_name
     "hdiff": dict(short_name="hdiff", relative_path="weather_stencils/hdiff", module_name="hdiff",
                   func_name="hdiff", input_args=["in_field", "out_field", "coeff"],
                   array_args=["in_field", "out_field", "coeff"], output_args=["out_field"]),
+    # widening row: bench_info/{jacobi_1d,seidel_2d}.json
+    "jacobi_1d": dict(short_name="jacobi1d", relative_path="polybench/jacobi_1d", module_name="jacobi_1d",
+                      func_name="kernel", input_args=["TSTEPS", "A", "B"], array_args=["A", "B"],
+                      output_args=["A", "B"]),
+    "seidel_2d": dict(short_name="seidel2d", relative_path="polybench/seidel_2d", module_name="seidel_2d",
+                      func_name="kernel", input_args=["TSTEPS", "N", "A"], array_args=["A"], output_args=["A"]),
     "vadv": dict(short_name="vadv", relative_path="weather_stencils/vadv", module_name="vadv", func_name="vadv",
                  input_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens", "dtr_stage"],
                  array_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens"], output_args=["utens_stage"]),

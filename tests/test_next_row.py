@@ -1,0 +1,161 @@
+"""Widening row: jacobi_1d and seidel_2d.
+
+CPU part: the oracle (oracle/stencil_oracle.c: npb_oracle_jacobi1d / npb_oracle_seidel2d) against outputs of the
+unmodified reference (jacobi_1d_numpy.py:4-8, seidel_2d_numpy.py:4-13; fixtures from
+tests/golden/make_golden_next.py).  GPU part (-m gpu): the CUDA kernels through the C ABI
+(npb_jacobi1d_f64, npb_seidel2d_f64) against the oracle and the fixtures.  Bar: bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, assert_bit_equal, sha
+
+
+@pytest.fixture(scope="module")
+def pins_next():
+    with open(os.path.join(GOLDEN, "pins_next.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def cases_next():
+    z = np.load(os.path.join(GOLDEN, "cases_next.npz"))
+    out = {}
+    for key in z.files:
+        bench, idx, field = key.split(".", 2)
+        out.setdefault(bench, {}).setdefault(int(idx), {})[field] = z[key]
+    return {b: [d[i] for i in sorted(d)] for b, d in out.items()}
+
+
+# ------------------------------------------------------------------ oracle (CPU)
+@pytest.mark.parametrize("preset", ["S", "M"])
+def test_oracle_jacobi_1d_presets(pins_next, preset):
+    p = oracle.PRESETS["jacobi_1d"][preset]; pin = pins_next["jacobi_1d/" + preset]
+    A, B = oracle.init_jacobi_1d(p["N"])
+    assert sha(A) == pin["in"]["A"]["sha256"] and sha(B) == pin["in"]["B"]["sha256"]
+    oracle.jacobi_1d(p["TSTEPS"], A, B)
+    assert sha(A) == pin["out"]["A"]["sha256"] and sha(B) == pin["out"]["B"]["sha256"]
+
+
+@pytest.mark.parametrize("preset", ["S", "M", "L"])
+def test_oracle_seidel_2d_presets(pins_next, preset):
+    p = oracle.PRESETS["seidel_2d"][preset]; pin = pins_next["seidel_2d/" + preset]
+    A = oracle.init_seidel_2d(p["N"])
+    assert sha(A) == pin["in"]["A"]["sha256"]
+    oracle.seidel_2d(p["TSTEPS"], p["N"], A)
+    assert sha(A) == pin["out"]["A"]["sha256"]
+
+
+def test_oracle_small_cases(cases_next):
+    for n, c in enumerate(cases_next["jacobi_1d"]):
+        A, B = c["A_in"].copy(), c["B_in"].copy()
+        oracle.jacobi_1d(int(c["TSTEPS"]), A, B)
+        assert_bit_equal(A, c["A_out"], "jacobi_1d.%d A" % n); assert_bit_equal(B, c["B_out"], "jacobi_1d.%d B" % n)
+    for n, c in enumerate(cases_next["seidel_2d"]):
+        A = c["A_in"].copy()
+        oracle.seidel_2d(int(c["TSTEPS"]), int(c["N"]), A)
+        assert_bit_equal(A, c["A_out"], "seidel_2d.%d" % n)
+
+
+# ------------------------------------------------------------------ CUDA kernels
+@pytest.fixture(scope="module")
+def nb():
+    import npbench_b200 as nb_
+    nb_.init(0)
+    return nb_
+
+
+def run_j1(nb, ts, A, B, host):
+    if host:
+        a, b = A.copy(), B.copy()
+        nb.jacobi_1d(ts, a, b)
+        return a, b
+    dA, dB = nb.DeviceArray.from_host(A), nb.DeviceArray.from_host(B)
+    nb.jacobi_1d(ts, dA, dB)
+    return dA.to_host(), dB.to_host()
+
+
+def run_s2(nb, ts, A, host):
+    if host:
+        a = A.copy()
+        nb.seidel_2d(ts, A.shape[0], a)
+        return a
+    dA = nb.DeviceArray.from_host(A)
+    nb.seidel_2d(ts, A.shape[0], dA)
+    return dA.to_host()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [False, True], ids=["device", "host"])
+def test_gpu_golden_cases(nb, cases_next, host):
+    for n, c in enumerate(cases_next["jacobi_1d"]):
+        A, B = run_j1(nb, int(c["TSTEPS"]), c["A_in"], c["B_in"], host)
+        assert_bit_equal(A, c["A_out"], "jacobi_1d.%d A" % n); assert_bit_equal(B, c["B_out"], "jacobi_1d.%d B" % n)
+    for n, c in enumerate(cases_next["seidel_2d"]):
+        A = run_s2(nb, int(c["TSTEPS"]), c["A_in"], host)
+        assert_bit_equal(A, c["A_out"], "seidel_2d.%d" % n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["S", "M", "L", "paper"])
+def test_gpu_jacobi_1d_presets(nb, pins_next, preset):
+    p = oracle.PRESETS["jacobi_1d"][preset]
+    A, B = oracle.init_jacobi_1d(p["N"])
+    gA, gB = run_j1(nb, p["TSTEPS"], A, B, host=False)
+    if "jacobi_1d/" + preset in pins_next:
+        pin = pins_next["jacobi_1d/" + preset]["out"]
+        assert sha(gA) == pin["A"]["sha256"] and sha(gB) == pin["B"]["sha256"]
+    oracle.set_threads(4)
+    try:
+        oracle.jacobi_1d(p["TSTEPS"], A, B)
+    finally:
+        oracle.set_threads(1)
+    assert_bit_equal(gA, A, "A"); assert_bit_equal(gB, B, "B")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["S", "M", "L", "paper"])
+def test_gpu_seidel_2d_presets(nb, pins_next, preset):
+    p = oracle.PRESETS["seidel_2d"][preset]
+    A = oracle.init_seidel_2d(p["N"])
+    gA = run_s2(nb, p["TSTEPS"], A, host=False)
+    if "seidel_2d/" + preset in pins_next:
+        assert sha(gA) == pins_next["seidel_2d/" + preset]["out"]["A"]["sha256"]
+    oracle.seidel_2d(p["TSTEPS"], p["N"], A)
+    assert_bit_equal(gA, A, "A")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ts,n", [(1, 10), (2, 3), (2, 2), (3, 1), (9, 31), (17, 32), (64, 33), (200, 777), (129, 4096),
+                                  (1000, 100), (4, 100000)])
+def test_gpu_jacobi_1d_random(nb, ts, n):
+    rng = np.random.default_rng(ts + n)
+    A, B = rng.random((n,)) - 0.5, rng.random((n,)) - 0.5
+    gA, gB = run_j1(nb, ts, A, B, host=False)
+    oracle.jacobi_1d(ts, A, B)
+    assert_bit_equal(gA, A, "A"); assert_bit_equal(gB, B, "B")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["dispatch", "l2"])
+@pytest.mark.parametrize("ts,n", [(1, 10), (2, 3), (2, 2), (2, 5), (3, 6), (7, 40), (30, 17), (5, 129), (3, 300), (12, 64),
+                                  (9, 24), (6, 25), (4, 440), (3, 470), (20, 97), (3, 500)])
+def test_gpu_seidel_2d_random(nb, ts, n, mode):
+    """mode 0: distributed-shared-memory cluster kernel when 24 <= N and the grid fits (else L2 kernel); 1: L2 kernel."""
+    rng = np.random.default_rng(ts * 100 + n)
+    A = rng.random((n, n)) - 0.5
+    nb.lib().seidel2d_set_mode(mode)
+    try:
+        gA = run_s2(nb, ts, A, host=False)
+        path = nb.lib().seidel2d_last_path()
+    finally:
+        nb.lib().seidel2d_set_mode(0)
+    if ts > 1 and n >= 3:
+        fits = n >= 24 and ((n + 7) // 8) * n * 8 + 1024 <= 232448          # one 8-CTA cluster's shared memory
+        assert path == (1 if (mode == 0 and fits) else 2)
+    oracle.seidel_2d(ts, n, A)
+    assert_bit_equal(gA, A, "A")

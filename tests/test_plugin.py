@@ -33,6 +33,8 @@ def test_plugin_modules_have_the_numpy_signatures():
     want = {"polybench/jacobi_2d/jacobi_2d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
             "polybench/heat_3d/heat_3d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
             "polybench/fdtd_2d/fdtd_2d_b200.py": ("kernel", ["TMAX", "ex", "ey", "hz", "_fict_"]),
+            "polybench/jacobi_1d/jacobi_1d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
+            "polybench/seidel_2d/seidel_2d_b200.py": ("kernel", ["TSTEPS", "N", "A"]),
             "weather_stencils/hdiff/hdiff_b200.py": ("hdiff", ["in_field", "out_field", "coeff"]),
             "weather_stencils/vadv/vadv_b200.py": ("vadv", ["utens_stage", "u_stage", "wcon", "u_pos", "utens",
                                                             "dtr_stage"])}
@@ -73,7 +75,7 @@ def test_b200_through_real_harness_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv"])
+@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d"])
 def test_plugin_end_to_end_with_standin_harness(bench):
     import harness_standin as hs
     infra = hs.install()
@@ -92,6 +94,12 @@ def test_plugin_end_to_end_with_standin_harness(bench):
         ex, ey, hz, f = oracle.init_fdtd_2d(p["TMAX"], p["NX"], p["NY"])
         bdata = dict(TMAX=p["TMAX"], ex=ex, ey=ey, hz=hz, _fict_=f)
         ref = lambda d: oracle.fdtd_2d(d["TMAX"], d["ex"], d["ey"], d["hz"], d["_fict_"])
+    elif bench == "jacobi_1d":
+        A, B = oracle.init_jacobi_1d(p["N"]); bdata = dict(TSTEPS=p["TSTEPS"], A=A, B=B)
+        ref = lambda d: oracle.jacobi_1d(d["TSTEPS"], d["A"], d["B"])
+    elif bench == "seidel_2d":
+        bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], A=oracle.init_seidel_2d(p["N"]))
+        ref = lambda d: oracle.seidel_2d(d["TSTEPS"], d["N"], d["A"])
     elif bench == "hdiff":
         i, o, c = oracle.init_hdiff(p["I"], p["J"], p["K"]); bdata = dict(in_field=i, out_field=o, coeff=c)
         ref = lambda d: oracle.hdiff(d["in_field"], d["out_field"], d["coeff"])

@@ -16,6 +16,8 @@ PRESETS = {
                 "big": (10, 8192, 16384)},
     "hdiff": {"S": (64, 64, 60), "M": (128, 128, 160), "L": (384, 384, 160), "paper": (256, 256, 160)},
     "vadv": {"S": (60, 60, 40), "M": (112, 112, 80), "L": (180, 180, 160), "paper": (256, 256, 160)},
+    "jacobi_1d": {"S": (800, 3200), "M": (3000, 12000), "L": (8500, 34000), "paper": (4000, 32000)},
+    "seidel_2d": {"S": (8, 50), "M": (15, 100), "L": (40, 200), "paper": (100, 400)},
 }
 
 
@@ -70,6 +72,16 @@ def main():
                 L.init_fdtd2d_f64(tm, nx, ny, 0, nx, *(x.ptr for x in a))
                 fn = lambda: nb.fdtd_2d(tm, *a)
                 units = tm * nx * ny; bpu = 48
+            elif bench == "jacobi_1d":
+                ts, n = p
+                A = nb.DeviceArray.from_host((np.arange(n) + 2.0) / n); B = nb.DeviceArray.from_host((np.arange(n) + 3.0) / n)
+                fn = lambda: nb.jacobi_1d(ts, A, B)
+                units = 2 * (ts - 1) * (n - 2); bpu = 16
+            elif bench == "seidel_2d":
+                ts, n = p
+                A = nb.DeviceArray.from_host(rng.random((n, n)))
+                fn = lambda: nb.seidel_2d(ts, n, A)
+                units = (ts - 1) * (n - 2) ** 2; bpu = 16
             elif bench == "hdiff":
                 I, J, K = p
                 a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]
