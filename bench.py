@@ -146,6 +146,8 @@ def units_of(bench, p):
         return 2 * (p["TSTEPS"] - 1) * (p["N"] - 2), 16.0
     if bench == "seidel_2d":      # one interior cell updated by one Gauss-Seidel sweep (in place: read 8 + write 8)
         return (p["TSTEPS"] - 1) * (p["N"] - 2) ** 2, 16.0
+    if bench == "adi":            # one interior cell solved by one directional sweep (two sweeps per time step)
+        return 2 * p["TSTEPS"] * (p["N"] - 2) ** 2, 16.0
     if bench == "hdiff":
         I, J, K = p["I"], p["J"], p["K"]
         return I * J * K, 8.0 * ((I + 4) * (J + 4) + 2 * I * J) / (I * J)
@@ -172,6 +174,9 @@ SUITE = [
     ("jacobi_1d", "L", dict(TSTEPS=8500, N=34000)), ("jacobi_1d", "paper", dict(TSTEPS=4000, N=32000)),
     ("seidel_2d", "S", dict(TSTEPS=8, N=50)), ("seidel_2d", "M", dict(TSTEPS=15, N=100)),
     ("seidel_2d", "L", dict(TSTEPS=40, N=200)), ("seidel_2d", "paper", dict(TSTEPS=100, N=400)),
+    # widening row rank 2
+    ("adi", "S", dict(TSTEPS=5, N=100)), ("adi", "M", dict(TSTEPS=20, N=200)),
+    ("adi", "L", dict(TSTEPS=50, N=500)), ("adi", "paper", dict(TSTEPS=100, N=200)),
 ]
 
 
@@ -201,6 +206,16 @@ def make_device_case(nb, bench, p, rng):
         i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
         A = nb.DeviceArray.from_host((i * (j + 2.0) + 2.0) / n)
         return (A,), (lambda: nb.seidel_2d(p["TSTEPS"], n, A))
+    if bench == "adi":            # adi.py: u = (i + N - j) / N
+        n = p["N"]
+        i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
+        u0 = nb.DeviceArray.from_host((i + n - j) / n)
+        u = nb.DeviceArray((n, n))
+
+        def step():     # the reference's coefficients make u grow by orders of magnitude per call: restart from u0 every time
+            L.d2d(u.ptr, u0.ptr, n * n * 8)
+            nb.adi(p["TSTEPS"], n, u)
+        return (u, u0), step
     I, J, K = p["I"], p["J"], p["K"]
     if bench == "hdiff":   # hdiff.py:6-15 draws U[0,1); any U[0,1) data has the same cost
         a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]

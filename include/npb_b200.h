@@ -155,6 +155,11 @@ int npb_seidel2d_f64_host(int64_t tsteps, int64_t n, double *A);
 int npb_seidel2d_set_mode(int mode);     /* 0 dispatch (distributed-shared-memory kernel when the grid fits in one cluster), 1 L2 wavefront kernel */
 int npb_seidel2d_last_path(void);        /* 1 distributed-shared-memory kernel, 2 L2 wavefront kernel */
 
+/* widening row, rank 2 -- kernel(TSTEPS, N, u): polybench/adi/adi_numpy.py:6-54.  u is (n, n), updated in place;
+ * TSTEPS >= 1 (the reference divides by it). */
+int npb_adi_f64(int64_t tsteps, int64_t n, double *u);
+int npb_adi_f64_host(int64_t tsteps, int64_t n, double *u);
+
 /* ---- device-side initialisers (NPBench `initialize`, closed forms):
  *      jacobi_2d.py:6-10, heat_3d.py:6-11, fdtd_2d.py:6-15.  Rows
  *      [row0, row0+nrows) of the global grid, for the scaled / sharded grids. */

@@ -108,3 +108,16 @@ def seidel_2d(TSTEPS, N, A):
     L = _lib.lib()
     fn = L.seidel2d_f64 if _kind(A) == "device" else L.seidel2d_f64_host
     fn(int(TSTEPS), int(N), _p(A))
+
+
+def adi(TSTEPS, N, u):
+    """kernel(TSTEPS, N, u) -- polybench/adi/adi_numpy.py:6-54; returns u like the reference (:54)."""
+    if len(u.shape) != 2 or u.shape[0] != u.shape[1] or u.shape[0] != int(N):
+        raise ValueError("u must be an (N, N) array")
+    if int(TSTEPS) == 0:
+        raise ZeroDivisionError("float division by zero")       # DT = 1.0 / TSTEPS, adi_numpy.py:14
+    L = _lib.lib()
+    if int(TSTEPS) > 0:
+        fn = L.adi_f64 if _kind(u) == "device" else L.adi_f64_host
+        fn(int(TSTEPS), int(N), _p(u))
+    return u

@@ -47,6 +47,8 @@ def lib():
         L.npb_oracle_init_jacobi1d.argtypes = [_i64, _dp, _dp]
         L.npb_oracle_seidel2d.argtypes = [_i64, _i64, _dp]
         L.npb_oracle_init_seidel2d.argtypes = [_i64, _dp]
+        L.npb_oracle_adi.argtypes = [_i64, _i64, _dp]
+        L.npb_oracle_init_adi.argtypes = [_i64, _dp]
         _LIB = L
     return _LIB
 
@@ -114,7 +116,22 @@ def seidel_2d(TSTEPS, N, A):
     lib().npb_oracle_seidel2d(int(TSTEPS), int(N), _ptr(A))
 
 
+def adi(TSTEPS, N, u):
+    """polybench/adi/adi_numpy.py:6-54 (mutates u like the reference, which also returns it)"""
+    assert u.shape == (N, N)
+    lib().npb_oracle_adi(int(TSTEPS), int(N), _ptr(u))
+    return u
+
+
 # -- initialisers (NPBench's `initialize` functions restated) ----------------
+
+def init_adi(N):
+    """adi.py: u = (i + N - j) / N"""
+    u = np.empty((N, N))
+    lib().npb_oracle_init_adi(N, _ptr(u))
+    return u
+
+
 
 def init_jacobi_1d(N):
     """jacobi_1d.py:6-10"""
@@ -195,4 +212,6 @@ PRESETS = {
                   "L": dict(TSTEPS=8500, N=34000), "paper": dict(TSTEPS=4000, N=32000)},
     "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100),
                   "L": dict(TSTEPS=40, N=200), "paper": dict(TSTEPS=100, N=400)},
+    "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200),
+            "L": dict(TSTEPS=50, N=500), "paper": dict(TSTEPS=100, N=200)},
 }

@@ -1,4 +1,4 @@
-"""Golden fixtures for the widening row: jacobi_1d and seidel_2d.
+"""Golden fixtures for the widening row: jacobi_1d, seidel_2d and (rank 2) adi.
 
     python tests/golden/make_golden_next.py            # needs /root/reference (read-only)
 
@@ -23,6 +23,7 @@ from make_golden import digest, ref  # noqa: E402  (also puts the reference on s
 PRESETS = {  # bench_info/{jacobi_1d,seidel_2d}.json "parameters"
     "jacobi_1d": {"S": dict(TSTEPS=800, N=3200), "M": dict(TSTEPS=3000, N=12000)},
     "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100), "L": dict(TSTEPS=40, N=200)},
+    "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200), "paper": dict(TSTEPS=100, N=200)},
 }
 
 
@@ -44,6 +45,15 @@ def main():
         s_kern(p["TSTEPS"], p["N"], A)
         e["out"] = {"A": digest(A)}
         pins["seidel_2d/" + preset] = e
+    a_init = ref("polybench/adi", "adi", "initialize")
+    a_kern = ref("polybench/adi", "adi_numpy", "kernel")
+    for preset, p in PRESETS["adi"].items():
+        u = a_init(p["N"])
+        e = {"in": {"u": digest(u)}}
+        r = a_kern(p["TSTEPS"], p["N"], u)
+        assert r is u
+        e["out"] = {"u": digest(u)}
+        pins["adi/" + preset] = e
     with open(os.path.join(HERE, "pins_next.json"), "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)
 
@@ -65,6 +75,12 @@ def main():
         A0 = A.copy()
         s_kern(ts, N, A)
         put("seidel_2d.%d" % n, TSTEPS=ts, N=N, A_in=A0, A_out=A)
+    # adi cases draw AFTER the others so that the earlier fixtures keep their values
+    for n, (ts, N) in enumerate([(1, 3), (1, 4), (2, 5), (3, 9), (4, 33), (7, 64), (2, 100), (5, 47)]):
+        u = rng.random((N, N)) - 0.5
+        u0 = u.copy()
+        a_kern(ts, N, u)
+        put("adi.%d" % n, TSTEPS=ts, N=N, u_in=u0, u_out=u)
     np.savez_compressed(os.path.join(HERE, "cases_next.npz"), **cases)
     print("pins:", len(pins) - 1, "cases arrays:", len(cases),
           "npz bytes:", os.path.getsize(os.path.join(HERE, "cases_next.npz")))

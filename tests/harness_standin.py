@@ -41,6 +41,8 @@ BENCH_INFO = {   # bench_info/<name>.json: relative_path, module_name, func_name
                       output_args=["A", "B"]),
     "seidel_2d": dict(short_name="seidel2d", relative_path="polybench/seidel_2d", module_name="seidel_2d",
                       func_name="kernel", input_args=["TSTEPS", "N", "A"], array_args=["A"], output_args=["A"]),
+    "adi": dict(short_name="adi", relative_path="polybench/adi", module_name="adi", func_name="kernel",
+                input_args=["TSTEPS", "N", "u"], array_args=["u"], output_args=["u"]),
     "vadv": dict(short_name="vadv", relative_path="weather_stencils/vadv", module_name="vadv", func_name="vadv",
                  input_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens", "dtr_stage"],
                  array_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens"], output_args=["utens_stage"]),

@@ -1,4 +1,4 @@
-"""Widening row: jacobi_1d and seidel_2d.
+"""Widening row: rank 1 jacobi_1d and seidel_2d, rank 2 adi.
 
 CPU part: the oracle (oracle/stencil_oracle.c: npb_oracle_jacobi1d / npb_oracle_seidel2d) against outputs of the
 unmodified reference (jacobi_1d_numpy.py:4-8, seidel_2d_numpy.py:4-13; fixtures from
@@ -50,7 +50,24 @@ def test_oracle_seidel_2d_presets(pins_next, preset):
     assert sha(A) == pin["out"]["A"]["sha256"]
 
 
+@pytest.mark.parametrize("preset", ["S", "M", "paper"])
+def test_oracle_adi_presets(pins_next, preset):
+    p = oracle.PRESETS["adi"][preset]; pin = pins_next["adi/" + preset]
+    u = oracle.init_adi(p["N"])
+    assert sha(u) == pin["in"]["u"]["sha256"]
+    oracle.set_threads(4)
+    try:
+        oracle.adi(p["TSTEPS"], p["N"], u)
+    finally:
+        oracle.set_threads(1)
+    assert sha(u) == pin["out"]["u"]["sha256"]
+
+
 def test_oracle_small_cases(cases_next):
+    for n, c in enumerate(cases_next["adi"]):
+        u = c["u_in"].copy()
+        oracle.adi(int(c["TSTEPS"]), int(c["N"]), u)
+        assert_bit_equal(u, c["u_out"], "adi.%d" % n)
     for n, c in enumerate(cases_next["jacobi_1d"]):
         A, B = c["A_in"].copy(), c["B_in"].copy()
         oracle.jacobi_1d(int(c["TSTEPS"]), A, B)
@@ -89,9 +106,55 @@ def run_s2(nb, ts, A, host):
     return dA.to_host()
 
 
+def run_adi(nb, ts, u, host):
+    if host:
+        a = u.copy()
+        r = nb.adi(ts, u.shape[0], a)
+        assert r is a                       # the reference returns its (mutated) argument: adi_numpy.py:54
+        return a
+    d = nb.DeviceArray.from_host(u)
+    assert nb.adi(ts, u.shape[0], d) is d
+    return d.to_host()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["S", "M", "L", "paper"])
+def test_gpu_adi_presets(nb, pins_next, preset):
+    p = oracle.PRESETS["adi"][preset]
+    u = oracle.init_adi(p["N"])
+    g = run_adi(nb, p["TSTEPS"], u, host=False)
+    if "adi/" + preset in pins_next:
+        assert sha(g) == pins_next["adi/" + preset]["out"]["u"]["sha256"]
+    oracle.set_threads(4)
+    try:
+        oracle.adi(p["TSTEPS"], p["N"], u)
+    finally:
+        oracle.set_threads(1)
+    assert_bit_equal(g, u, "u")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ts,n", [(1, 3), (1, 2), (2, 4), (3, 31), (2, 32), (4, 33), (6, 65), (3, 257), (9, 100)])
+def test_gpu_adi_random(nb, ts, n):
+    rng = np.random.default_rng(ts * 1000 + n)
+    u = rng.random((n, n)) - 0.5
+    g = run_adi(nb, ts, u, host=False)
+    oracle.adi(ts, n, u)
+    assert_bit_equal(g, u, "u")
+
+
+@pytest.mark.gpu
+def test_gpu_adi_zero_steps_raises_like_the_reference(nb):
+    with pytest.raises(ZeroDivisionError):          # DT = 1.0 / TSTEPS, adi_numpy.py:14
+        nb.adi(0, 8, np.zeros((8, 8)))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("host", [False, True], ids=["device", "host"])
 def test_gpu_golden_cases(nb, cases_next, host):
+    for n, c in enumerate(cases_next["adi"]):
+        g = run_adi(nb, int(c["TSTEPS"]), c["u_in"], host)
+        assert_bit_equal(g, c["u_out"], "adi.%d" % n)
     for n, c in enumerate(cases_next["jacobi_1d"]):
         A, B = run_j1(nb, int(c["TSTEPS"]), c["A_in"], c["B_in"], host)
         assert_bit_equal(A, c["A_out"], "jacobi_1d.%d A" % n); assert_bit_equal(B, c["B_out"], "jacobi_1d.%d B" % n)

@@ -35,6 +35,7 @@ def test_plugin_modules_have_the_numpy_signatures():
             "polybench/fdtd_2d/fdtd_2d_b200.py": ("kernel", ["TMAX", "ex", "ey", "hz", "_fict_"]),
             "polybench/jacobi_1d/jacobi_1d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
             "polybench/seidel_2d/seidel_2d_b200.py": ("kernel", ["TSTEPS", "N", "A"]),
+            "polybench/adi/adi_b200.py": ("kernel", ["TSTEPS", "N", "u"]),
             "weather_stencils/hdiff/hdiff_b200.py": ("hdiff", ["in_field", "out_field", "coeff"]),
             "weather_stencils/vadv/vadv_b200.py": ("vadv", ["utens_stage", "u_stage", "wcon", "u_pos", "utens",
                                                             "dtr_stage"])}
@@ -75,7 +76,7 @@ def test_b200_through_real_harness_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d"])
+@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d", "adi"])
 def test_plugin_end_to_end_with_standin_harness(bench):
     import harness_standin as hs
     infra = hs.install()
@@ -100,6 +101,9 @@ def test_plugin_end_to_end_with_standin_harness(bench):
     elif bench == "seidel_2d":
         bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], A=oracle.init_seidel_2d(p["N"]))
         ref = lambda d: oracle.seidel_2d(d["TSTEPS"], d["N"], d["A"])
+    elif bench == "adi":
+        bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], u=oracle.init_adi(p["N"]))
+        ref = lambda d: oracle.adi(d["TSTEPS"], d["N"], d["u"])
     elif bench == "hdiff":
         i, o, c = oracle.init_hdiff(p["I"], p["J"], p["K"]); bdata = dict(in_field=i, out_field=o, coeff=c)
         ref = lambda d: oracle.hdiff(d["in_field"], d["out_field"], d["coeff"])
@@ -110,8 +114,10 @@ def test_plugin_end_to_end_with_standin_harness(bench):
     impl, _ = frm.implementations(b)[0]
     assert "__npb_b200_sync()" in frm.exec_str(b, impl) and "__npb_b200_sync()" in frm.setup_str(b, impl)
     out, times = hs.execute(frm, b, impl, bdata, repeat=3)
-    assert len(times) == 3 and len(out) == len(b.info["output_args"])
-    got = [frm.copy_back_func()(a) for a in out]
+    nout = len(b.info["output_args"])
+    # adi returns its argument like the reference does (adi_numpy.py:54): returned values come first (test.py:39-50)
+    assert len(times) == 3 and len(out) == nout + (1 if bench == "adi" else 0)
+    got = [frm.copy_back_func()(a) for a in out[-nout:]]
     want = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in bdata.items()}
     ref(want)
     for name, g in zip(b.info["output_args"], got):

@@ -18,6 +18,7 @@ PRESETS = {
     "vadv": {"S": (60, 60, 40), "M": (112, 112, 80), "L": (180, 180, 160), "paper": (256, 256, 160)},
     "jacobi_1d": {"S": (800, 3200), "M": (3000, 12000), "L": (8500, 34000), "paper": (4000, 32000)},
     "seidel_2d": {"S": (8, 50), "M": (15, 100), "L": (40, 200), "paper": (100, 400)},
+    "adi": {"S": (5, 100), "M": (20, 200), "L": (50, 500), "paper": (100, 200)},
 }
 
 
@@ -82,6 +83,11 @@ def main():
                 A = nb.DeviceArray.from_host(rng.random((n, n)))
                 fn = lambda: nb.seidel_2d(ts, n, A)
                 units = (ts - 1) * (n - 2) ** 2; bpu = 16
+            elif bench == "adi":
+                ts, n = p
+                A0 = nb.DeviceArray.from_host(rng.random((n, n))); A = nb.DeviceArray((n, n))
+                fn = lambda: (L.d2d(A.ptr, A0.ptr, n * n * 8), nb.adi(ts, n, A))    # the reference scheme diverges: restart every call
+                units = 2 * ts * (n - 2) ** 2; bpu = 16
             elif bench == "hdiff":
                 I, J, K = p
                 a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]
