@@ -146,6 +146,8 @@ def units_of(bench, p):
         return 2 * (p["TSTEPS"] - 1) * (p["N"] - 2), 16.0
     if bench == "seidel_2d":      # one interior cell updated by one Gauss-Seidel sweep (in place: read 8 + write 8)
         return (p["TSTEPS"] - 1) * (p["N"] - 2) ** 2, 16.0
+    if bench == "cavity_flow":    # one interior cell updated by one pass: per time step nit pressure iterations + b + (u, v)
+        return p["nt"] * (p["nit"] + 2) * (p["nx"] - 2) * (p["ny"] - 2), 16.0
     if bench == "adi":            # one interior cell solved by one directional sweep (two sweeps per time step)
         return 2 * p["TSTEPS"] * (p["N"] - 2) ** 2, 16.0
     if bench == "hdiff":
@@ -174,6 +176,9 @@ SUITE = [
     ("jacobi_1d", "L", dict(TSTEPS=8500, N=34000)), ("jacobi_1d", "paper", dict(TSTEPS=4000, N=32000)),
     ("seidel_2d", "S", dict(TSTEPS=8, N=50)), ("seidel_2d", "M", dict(TSTEPS=15, N=100)),
     ("seidel_2d", "L", dict(TSTEPS=40, N=200)), ("seidel_2d", "paper", dict(TSTEPS=100, N=400)),
+    # widening row rank 3
+    ("cavity_flow", "S", dict(ny=61, nx=61, nt=25, nit=5)), ("cavity_flow", "M", dict(ny=121, nx=121, nt=50, nit=10)),
+    ("cavity_flow", "L", dict(ny=201, nx=201, nt=100, nit=20)), ("cavity_flow", "paper", dict(ny=101, nx=101, nt=700, nit=50)),
     # widening row rank 2
     ("adi", "S", dict(TSTEPS=5, N=100)), ("adi", "M", dict(TSTEPS=20, N=200)),
     ("adi", "L", dict(TSTEPS=50, N=500)), ("adi", "paper", dict(TSTEPS=100, N=200)),
@@ -206,6 +211,18 @@ def make_device_case(nb, bench, p, rng):
         i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
         A = nb.DeviceArray.from_host((i * (j + 2.0) + 2.0) / n)
         return (A,), (lambda: nb.seidel_2d(p["TSTEPS"], n, A))
+    if bench == "cavity_flow":    # cavity_flow.py:6-13: zero fields, dx = 2/(nx-1), dy = 2/(ny-1), dt = .1/((nx-1)(ny-1))
+        nx, ny = p["nx"], p["ny"]
+        z = np.zeros((ny, nx))
+        f0 = [nb.DeviceArray.from_host(z) for _ in range(3)]
+        f = [nb.DeviceArray((ny, nx)) for _ in range(3)]
+        dx, dy, dt = 2 / (nx - 1), 2 / (ny - 1), .1 / ((nx - 1) * (ny - 1))
+
+        def step():     # restart from the initial fields like the harness does (copy_func in setup_str)
+            for x, x0 in zip(f, f0):
+                L.d2d(x.ptr, x0.ptr, nx * ny * 8)
+            nb.cavity_flow(nx, ny, p["nt"], p["nit"], f[0], f[1], dt, dx, dy, f[2], 1.0, 0.1)
+        return (f, f0), step
     if bench == "adi":            # adi.py: u = (i + N - j) / N
         n = p["N"]
         i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")

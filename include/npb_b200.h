@@ -160,6 +160,13 @@ int npb_seidel2d_last_path(void);        /* 1 distributed-shared-memory kernel, 
 int npb_adi_f64(int64_t tsteps, int64_t n, double *u);
 int npb_adi_f64_host(int64_t tsteps, int64_t n, double *u);
 
+/* widening row, rank 3 -- cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu):
+ * cavity_flow/cavity_flow_numpy.py:46-89.  u, v, p are (ny, nx), updated in place; nx, ny >= 3. */
+int npb_cavity_flow_f64(int64_t nx, int64_t ny, int64_t nt, int64_t nit, double *u, double *v, double dt, double dx,
+                        double dy, double *p, double rho, double nu);
+int npb_cavity_flow_f64_host(int64_t nx, int64_t ny, int64_t nt, int64_t nit, double *u, double *v, double dt, double dx,
+                             double dy, double *p, double rho, double nu);
+
 /* ---- device-side initialisers (NPBench `initialize`, closed forms):
  *      jacobi_2d.py:6-10, heat_3d.py:6-11, fdtd_2d.py:6-15.  Rows
  *      [row0, row0+nrows) of the global grid, for the scaled / sharded grids. */

@@ -121,3 +121,15 @@ def adi(TSTEPS, N, u):
         fn = L.adi_f64 if _kind(u) == "device" else L.adi_f64_host
         fn(int(TSTEPS), int(N), _p(u))
     return u
+
+
+def cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu):
+    """cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu) -- cavity_flow/cavity_flow_numpy.py:46-89."""
+    shape = (int(ny), int(nx))
+    if tuple(u.shape) != shape or tuple(v.shape) != shape or tuple(p.shape) != shape:
+        raise ValueError("u, v and p must be (ny, nx) arrays")
+    if int(nx) < 3 or int(ny) < 3:
+        raise ValueError("nx and ny must be >= 3")
+    L = _lib.lib()
+    fn = L.cavity_flow_f64 if _kind(u, v, p) == "device" else L.cavity_flow_f64_host
+    fn(int(nx), int(ny), int(nt), int(nit), _p(u), _p(v), float(dt), float(dx), float(dy), _p(p), float(rho), float(nu))

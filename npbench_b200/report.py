@@ -43,6 +43,9 @@ BENCH = {
     "seidel_2d": dict(short="seidel2d", kind="microbench", domain="Solver",
                       presets={"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100),
                                "L": dict(TSTEPS=40, N=200), "paper": dict(TSTEPS=100, N=400)}),
+    "cavity_flow": dict(short="cavtflow", kind="microapp", domain="Physics",
+                        presets={"S": dict(ny=61, nx=61, nt=25, nit=5), "M": dict(ny=121, nx=121, nt=50, nit=10),
+                                 "L": dict(ny=201, nx=201, nt=100, nit=20), "paper": dict(ny=101, nx=101, nt=700, nit=50)}),
     "adi": dict(short="adi", kind="microbench", domain="Solver",
                 presets={"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200),
                          "L": dict(TSTEPS=50, N=500), "paper": dict(TSTEPS=100, N=200)}),
@@ -104,6 +107,8 @@ def units_and_bytes(bench: str, p: dict):
         return float((p["TSTEPS"] - 1) * (p["N"] - 2) ** 2), 16.0
     if bench == "adi":
         return 2.0 * p["TSTEPS"] * (p["N"] - 2) ** 2, 16.0
+    if bench == "cavity_flow":
+        return float(p["nt"] * (p["nit"] + 2) * (p["nx"] - 2) * (p["ny"] - 2)), 16.0
     raise KeyError(bench)
 
 

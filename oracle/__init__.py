@@ -49,6 +49,8 @@ def lib():
         L.npb_oracle_init_seidel2d.argtypes = [_i64, _dp]
         L.npb_oracle_adi.argtypes = [_i64, _i64, _dp]
         L.npb_oracle_init_adi.argtypes = [_i64, _dp]
+        L.npb_oracle_cavity_flow.argtypes = [_i64, _i64, _i64, _i64, _dp, _dp, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, _dp, ctypes.c_double, ctypes.c_double]
         _LIB = L
     return _LIB
 
@@ -123,7 +125,21 @@ def adi(TSTEPS, N, u):
     return u
 
 
+def cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu):
+    """cavity_flow/cavity_flow_numpy.py:46-89"""
+    assert u.shape == (ny, nx) and v.shape == (ny, nx) and p.shape == (ny, nx) and nx >= 3 and ny >= 3
+    lib().npb_oracle_cavity_flow(int(nx), int(ny), int(nt), int(nit), _ptr(u), _ptr(v), float(dt), float(dx), float(dy),
+                                 _ptr(p), float(rho), float(nu))
+
+
 # -- initialisers (NPBench's `initialize` functions restated) ----------------
+
+def init_cavity_flow(ny, nx):
+    """cavity_flow/cavity_flow.py:6-13 -> u, v, p, dx, dy, dt"""
+    u = np.zeros((ny, nx)); v = np.zeros((ny, nx)); p = np.zeros((ny, nx))
+    return u, v, p, 2 / (nx - 1), 2 / (ny - 1), .1 / ((nx - 1) * (ny - 1))
+
+
 
 def init_adi(N):
     """adi.py: u = (i + N - j) / N"""
@@ -212,6 +228,9 @@ PRESETS = {
                   "L": dict(TSTEPS=8500, N=34000), "paper": dict(TSTEPS=4000, N=32000)},
     "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100),
                   "L": dict(TSTEPS=40, N=200), "paper": dict(TSTEPS=100, N=400)},
+    "cavity_flow": {"S": dict(ny=61, nx=61, nt=25, nit=5, rho=1.0, nu=0.1), "M": dict(ny=121, nx=121, nt=50, nit=10, rho=1.0, nu=0.1),
+                    "L": dict(ny=201, nx=201, nt=100, nit=20, rho=1.0, nu=0.1),
+                    "paper": dict(ny=101, nx=101, nt=700, nit=50, rho=1.0, nu=0.1)},
     "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200),
             "L": dict(TSTEPS=50, N=500), "paper": dict(TSTEPS=100, N=200)},
 }

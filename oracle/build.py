@@ -19,7 +19,7 @@ def build(force: bool = False) -> str:
             and os.path.getmtime(OUT) >= os.path.getmtime(SRC)):
         return OUT
     cmd = ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-fopenmp",
-           "-ffp-contract=off", "-fno-fast-math", "-o", OUT, SRC]
+           "-ffp-contract=off", "-fno-fast-math", "-fno-builtin-pow", "-o", OUT, SRC, "-lm"]
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -24,6 +24,7 @@ PRESETS = {  # bench_info/{jacobi_1d,seidel_2d}.json "parameters"
     "jacobi_1d": {"S": dict(TSTEPS=800, N=3200), "M": dict(TSTEPS=3000, N=12000)},
     "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100), "L": dict(TSTEPS=40, N=200)},
     "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200), "paper": dict(TSTEPS=100, N=200)},
+    "cavity_flow": {"S": dict(ny=61, nx=61, nt=25, nit=5, rho=1.0, nu=0.1), "M": dict(ny=121, nx=121, nt=50, nit=10, rho=1.0, nu=0.1)},
 }
 
 
@@ -54,6 +55,14 @@ def main():
         assert r is u
         e["out"] = {"u": digest(u)}
         pins["adi/" + preset] = e
+    c_init = ref("cavity_flow", "cavity_flow", "initialize")
+    c_kern = ref("cavity_flow", "cavity_flow_numpy", "cavity_flow")
+    for preset, p in PRESETS["cavity_flow"].items():
+        u, v, pr, dx, dy, dt = c_init(p["ny"], p["nx"])
+        e = {"in": {"u": digest(u), "v": digest(v), "p": digest(pr)}, "dx": dx, "dy": dy, "dt": dt}
+        c_kern(p["nx"], p["ny"], p["nt"], p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"])
+        e["out"] = {"u": digest(u), "v": digest(v), "p": digest(pr)}
+        pins["cavity_flow/" + preset] = e
     with open(os.path.join(HERE, "pins_next.json"), "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)
 
@@ -81,6 +90,15 @@ def main():
         u0 = u.copy()
         a_kern(ts, N, u)
         put("adi.%d" % n, TSTEPS=ts, N=N, u_in=u0, u_out=u)
+    # cavity_flow cases draw after everything else; random (not physical) fields, rectangular grids, nit/nt edge values
+    for n, (nx, ny, nt, nit) in enumerate([(3, 3, 1, 1), (5, 4, 2, 3), (9, 7, 3, 0), (17, 33, 4, 5), (40, 21, 0, 3),
+                                           (64, 64, 3, 7), (31, 50, 5, 2)]):
+        u, v, pr = rng.random((ny, nx)) - 0.5, rng.random((ny, nx)) - 0.5, rng.random((ny, nx)) - 0.5
+        dx, dy = 2 / (nx - 1), 2 / (ny - 1)
+        dt = .1 / ((nx - 1) * (ny - 1))
+        i = dict(u_in=u.copy(), v_in=v.copy(), p_in=pr.copy())
+        c_kern(nx, ny, nt, nit, u, v, dt, dx, dy, pr, 1.3, 0.07)
+        put("cavity_flow.%d" % n, nx=nx, ny=ny, nt=nt, nit=nit, dt=dt, dx=dx, dy=dy, rho=1.3, nu=0.07, u_out=u, v_out=v, p_out=pr, **i)
     np.savez_compressed(os.path.join(HERE, "cases_next.npz"), **cases)
     print("pins:", len(pins) - 1, "cases arrays:", len(cases),
           "npz bytes:", os.path.getsize(os.path.join(HERE, "cases_next.npz")))

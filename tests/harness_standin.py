@@ -43,6 +43,10 @@ BENCH_INFO = {   # bench_info/<name>.json: relative_path, module_name, func_name
                       func_name="kernel", input_args=["TSTEPS", "N", "A"], array_args=["A"], output_args=["A"]),
     "adi": dict(short_name="adi", relative_path="polybench/adi", module_name="adi", func_name="kernel",
                 input_args=["TSTEPS", "N", "u"], array_args=["u"], output_args=["u"]),
+    "cavity_flow": dict(short_name="cavtflow", relative_path="cavity_flow", module_name="cavity_flow",
+                        func_name="cavity_flow",
+                        input_args=["nx", "ny", "nt", "nit", "u", "v", "dt", "dx", "dy", "p", "rho", "nu"],
+                        array_args=["u", "v", "p"], output_args=["u", "v", "p"]),
     "vadv": dict(short_name="vadv", relative_path="weather_stencils/vadv", module_name="vadv", func_name="vadv",
                  input_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens", "dtr_stage"],
                  array_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens"], output_args=["utens_stage"]),

@@ -63,7 +63,27 @@ def test_oracle_adi_presets(pins_next, preset):
     assert sha(u) == pin["out"]["u"]["sha256"]
 
 
+@pytest.mark.parametrize("preset", ["S", "M"])
+def test_oracle_cavity_flow_presets(pins_next, preset):
+    p = oracle.PRESETS["cavity_flow"][preset]; pin = pins_next["cavity_flow/" + preset]
+    u, v, pr, dx, dy, dt = oracle.init_cavity_flow(p["ny"], p["nx"])
+    assert (dx, dy, dt) == (pin["dx"], pin["dy"], pin["dt"])
+    oracle.set_threads(4)
+    try:
+        oracle.cavity_flow(p["nx"], p["ny"], p["nt"], p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"])
+    finally:
+        oracle.set_threads(1)
+    for name, a in (("u", u), ("v", v), ("p", pr)):
+        assert sha(a) == pin["out"][name]["sha256"], name
+
+
 def test_oracle_small_cases(cases_next):
+    for n, c in enumerate(cases_next["cavity_flow"]):
+        u, v, pr = c["u_in"].copy(), c["v_in"].copy(), c["p_in"].copy()
+        oracle.cavity_flow(int(c["nx"]), int(c["ny"]), int(c["nt"]), int(c["nit"]), u, v, float(c["dt"]), float(c["dx"]),
+                           float(c["dy"]), pr, float(c["rho"]), float(c["nu"]))
+        for name, a in (("u", u), ("v", v), ("p", pr)):
+            assert_bit_equal(a, c[name + "_out"], "cavity_flow.%d %s" % (n, name))
     for n, c in enumerate(cases_next["adi"]):
         u = c["u_in"].copy()
         oracle.adi(int(c["TSTEPS"]), int(c["N"]), u)
@@ -141,6 +161,46 @@ def test_gpu_adi_random(nb, ts, n):
     g = run_adi(nb, ts, u, host=False)
     oracle.adi(ts, n, u)
     assert_bit_equal(g, u, "u")
+
+
+def run_cavity(nb, c, host):
+    args = (int(c["nx"]), int(c["ny"]), int(c["nt"]), int(c["nit"]))
+    sc = (float(c["dt"]), float(c["dx"]), float(c["dy"]))
+    if host:
+        u, v, p = c["u_in"].copy(), c["v_in"].copy(), c["p_in"].copy()
+        nb.cavity_flow(*args, u, v, *sc, p, float(c["rho"]), float(c["nu"]))
+        return u, v, p
+    u, v, p = (nb.DeviceArray.from_host(c[k]) for k in ("u_in", "v_in", "p_in"))
+    nb.cavity_flow(*args, u, v, *sc, p, float(c["rho"]), float(c["nu"]))
+    return u.to_host(), v.to_host(), p.to_host()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [False, True], ids=["device", "host"])
+def test_gpu_cavity_flow_golden_cases(nb, cases_next, host):
+    for n, c in enumerate(cases_next["cavity_flow"]):
+        for name, g in zip(("u", "v", "p"), run_cavity(nb, c, host)):
+            assert_bit_equal(g, c[name + "_out"], "cavity_flow.%d %s" % (n, name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["S", "M", "L", "paper"])
+def test_gpu_cavity_flow_presets(nb, pins_next, preset):
+    p = oracle.PRESETS["cavity_flow"][preset]
+    u, v, pr, dx, dy, dt = oracle.init_cavity_flow(p["ny"], p["nx"])
+    c = dict(nx=p["nx"], ny=p["ny"], nt=p["nt"], nit=p["nit"], dt=dt, dx=dx, dy=dy, rho=p["rho"], nu=p["nu"],
+             u_in=u, v_in=v, p_in=pr)
+    for _ in range(2):                                       # second call replays the cached graph
+        gu, gv, gp = run_cavity(nb, c, host=False)
+    if "cavity_flow/" + preset in pins_next:
+        pin = pins_next["cavity_flow/" + preset]["out"]
+        assert (sha(gu), sha(gv), sha(gp)) == (pin["u"]["sha256"], pin["v"]["sha256"], pin["p"]["sha256"])
+    oracle.set_threads(8)
+    try:
+        oracle.cavity_flow(p["nx"], p["ny"], p["nt"], p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"])
+    finally:
+        oracle.set_threads(1)
+    assert_bit_equal(gu, u, "u"); assert_bit_equal(gv, v, "v"); assert_bit_equal(gp, pr, "p")
 
 
 @pytest.mark.gpu

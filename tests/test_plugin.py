@@ -36,6 +36,8 @@ def test_plugin_modules_have_the_numpy_signatures():
             "polybench/jacobi_1d/jacobi_1d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
             "polybench/seidel_2d/seidel_2d_b200.py": ("kernel", ["TSTEPS", "N", "A"]),
             "polybench/adi/adi_b200.py": ("kernel", ["TSTEPS", "N", "u"]),
+            "cavity_flow/cavity_flow_b200.py": ("cavity_flow", ["nx", "ny", "nt", "nit", "u", "v", "dt", "dx", "dy", "p",
+                                                                "rho", "nu"]),
             "weather_stencils/hdiff/hdiff_b200.py": ("hdiff", ["in_field", "out_field", "coeff"]),
             "weather_stencils/vadv/vadv_b200.py": ("vadv", ["utens_stage", "u_stage", "wcon", "u_pos", "utens",
                                                             "dtr_stage"])}
@@ -76,7 +78,7 @@ def test_b200_through_real_harness_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d", "adi"])
+@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d", "adi", "cavity_flow"])
 def test_plugin_end_to_end_with_standin_harness(bench):
     import harness_standin as hs
     infra = hs.install()
@@ -101,6 +103,12 @@ def test_plugin_end_to_end_with_standin_harness(bench):
     elif bench == "seidel_2d":
         bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], A=oracle.init_seidel_2d(p["N"]))
         ref = lambda d: oracle.seidel_2d(d["TSTEPS"], d["N"], d["A"])
+    elif bench == "cavity_flow":
+        u, v, pr, dx, dy, dt = oracle.init_cavity_flow(p["ny"], p["nx"])
+        bdata = dict(nx=p["nx"], ny=p["ny"], nt=p["nt"], nit=p["nit"], u=u, v=v, dt=dt, dx=dx, dy=dy, p=pr, rho=p["rho"],
+                     nu=p["nu"])
+        ref = lambda d: oracle.cavity_flow(d["nx"], d["ny"], d["nt"], d["nit"], d["u"], d["v"], d["dt"], d["dx"], d["dy"],
+                                           d["p"], d["rho"], d["nu"])
     elif bench == "adi":
         bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], u=oracle.init_adi(p["N"]))
         ref = lambda d: oracle.adi(d["TSTEPS"], d["N"], d["u"])

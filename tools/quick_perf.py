@@ -19,6 +19,7 @@ PRESETS = {
     "jacobi_1d": {"S": (800, 3200), "M": (3000, 12000), "L": (8500, 34000), "paper": (4000, 32000)},
     "seidel_2d": {"S": (8, 50), "M": (15, 100), "L": (40, 200), "paper": (100, 400)},
     "adi": {"S": (5, 100), "M": (20, 200), "L": (50, 500), "paper": (100, 200)},
+    "cavity_flow": {"S": (61, 25, 5), "M": (121, 50, 10), "L": (201, 100, 20), "paper": (101, 700, 50)},
 }
 
 
@@ -88,6 +89,16 @@ def main():
                 A0 = nb.DeviceArray.from_host(rng.random((n, n))); A = nb.DeviceArray((n, n))
                 fn = lambda: (L.d2d(A.ptr, A0.ptr, n * n * 8), nb.adi(ts, n, A))    # the reference scheme diverges: restart every call
                 units = 2 * ts * (n - 2) ** 2; bpu = 16
+            elif bench == "cavity_flow":
+                n, nt, nit = p
+                z = np.zeros((n, n)); a0 = [nb.DeviceArray.from_host(z) for _ in range(3)]; a = [nb.DeviceArray((n, n)) for _ in range(3)]
+                dx = 2 / (n - 1); dt = .1 / ((n - 1) * (n - 1))
+
+                def fn(a=a, a0=a0, n=n, nt=nt, nit=nit, dx=dx, dt=dt):
+                    for x, x0 in zip(a, a0):
+                        L.d2d(x.ptr, x0.ptr, n * n * 8)
+                    nb.cavity_flow(n, n, nt, nit, a[0], a[1], dt, dx, dx, a[2], 1.0, 0.1)
+                units = nt * (nit + 2) * (n - 2) ** 2; bpu = 16
             elif bench == "hdiff":
                 I, J, K = p
                 a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]
