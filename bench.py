@@ -146,6 +146,8 @@ def units_of(bench, p):
         return 2 * (p["TSTEPS"] - 1) * (p["N"] - 2), 16.0
     if bench == "seidel_2d":      # one interior cell updated by one Gauss-Seidel sweep (in place: read 8 + write 8)
         return (p["TSTEPS"] - 1) * (p["N"] - 2) ** 2, 16.0
+    if bench == "channel_flow":   # as cavity_flow, periodic in x: (ny-2) rows x nx columns per pass; steps = the returned count
+        return p.get("steps", 1) * (p["nit"] + 2) * p["nx"] * (p["ny"] - 2), 16.0
     if bench == "cavity_flow":    # one interior cell updated by one pass: per time step nit pressure iterations + b + (u, v)
         return p["nt"] * (p["nit"] + 2) * (p["nx"] - 2) * (p["ny"] - 2), 16.0
     if bench == "adi":            # one interior cell solved by one directional sweep (two sweeps per time step)
@@ -177,6 +179,8 @@ SUITE = [
     ("seidel_2d", "S", dict(TSTEPS=8, N=50)), ("seidel_2d", "M", dict(TSTEPS=15, N=100)),
     ("seidel_2d", "L", dict(TSTEPS=40, N=200)), ("seidel_2d", "paper", dict(TSTEPS=100, N=400)),
     # widening row rank 3
+    ("channel_flow", "S", dict(ny=61, nx=61, nit=5)), ("channel_flow", "M", dict(ny=121, nx=121, nit=10)),
+    ("channel_flow", "L", dict(ny=201, nx=201, nit=20)), ("channel_flow", "paper", dict(ny=101, nx=101, nit=50)),
     ("cavity_flow", "S", dict(ny=61, nx=61, nt=25, nit=5)), ("cavity_flow", "M", dict(ny=121, nx=121, nt=50, nit=10)),
     ("cavity_flow", "L", dict(ny=201, nx=201, nt=100, nit=20)), ("cavity_flow", "paper", dict(ny=101, nx=101, nt=700, nit=50)),
     # widening row rank 2
@@ -211,6 +215,17 @@ def make_device_case(nb, bench, p, rng):
         i, j = np.meshgrid(np.arange(n, dtype=np.float64), np.arange(n, dtype=np.float64), indexing="ij")
         A = nb.DeviceArray.from_host((i * (j + 2.0) + 2.0) / n)
         return (A,), (lambda: nb.seidel_2d(p["TSTEPS"], n, A))
+    if bench == "channel_flow":   # channel_flow.py: u = v = 0, p = 1
+        nx, ny = p["nx"], p["ny"]
+        f0 = [nb.DeviceArray.from_host(a) for a in (np.zeros((ny, nx)), np.zeros((ny, nx)), np.ones((ny, nx)))]
+        f = [nb.DeviceArray((ny, nx)) for _ in range(3)]
+        dx, dy, dt = 2 / (nx - 1), 2 / (ny - 1), .1 / ((nx - 1) * (ny - 1))
+
+        def step():     # restart from the initial fields; the call blocks until the flow has converged
+            for x, x0 in zip(f, f0):
+                L.d2d(x.ptr, x0.ptr, nx * ny * 8)
+            p["steps"] = nb.channel_flow(p["nit"], f[0], f[1], dt, dx, dy, f[2], 1.0, 0.1, 1.0)
+        return (f, f0), step
     if bench == "cavity_flow":    # cavity_flow.py:6-13: zero fields, dx = 2/(nx-1), dy = 2/(ny-1), dt = .1/((nx-1)(ny-1))
         nx, ny = p["nx"], p["ny"]
         z = np.zeros((ny, nx))
@@ -249,9 +264,9 @@ def run_suite(nb, peak):
     for bench, preset, p in SUITE:
         try:
             keep, step = make_device_case(nb, bench, p, rng)
-            units, bpu = units_of(bench, p)
             n0 = L.launch_count()
             step(); L.sync()
+            units, bpu = units_of(bench, p)
             launches = int(L.launch_count() - n0)
             est = dev_timer(L, step)
             reps = 3 if est > 20 else (5 if est > 2 else 15)

@@ -167,6 +167,13 @@ int npb_cavity_flow_f64(int64_t nx, int64_t ny, int64_t nt, int64_t nit, double 
 int npb_cavity_flow_f64_host(int64_t nx, int64_t ny, int64_t nt, int64_t nit, double *u, double *v, double dt, double dx,
                              double dy, double *p, double rho, double nu);
 
+/* channel_flow(nit, u, v, dt, dx, dy, p, rho, nu, F) -> stepcount: channel_flow/channel_flow_numpy.py:74-170.
+ * u, v, p are (ny, nx), updated in place; the call blocks (the convergence test needs one double per step). */
+int npb_channel_flow_f64(int64_t nit, int64_t nx, int64_t ny, double *u, double *v, double dt, double dx, double dy,
+                         double *p, double rho, double nu, double F, int64_t *stepcount);
+int npb_channel_flow_f64_host(int64_t nit, int64_t nx, int64_t ny, double *u, double *v, double dt, double dx, double dy,
+                              double *p, double rho, double nu, double F, int64_t *stepcount);
+
 /* ---- device-side initialisers (NPBench `initialize`, closed forms):
  *      jacobi_2d.py:6-10, heat_3d.py:6-11, fdtd_2d.py:6-15.  Rows
  *      [row0, row0+nrows) of the global grid, for the scaled / sharded grids. */

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "npb_seidel2d_last_path": (_int, []),
     "npb_cavity_flow_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp, _dbl, _dbl]),
     "npb_cavity_flow_f64_host": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp, _dbl, _dbl]),
+    "npb_channel_flow_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _vp]),
+    "npb_channel_flow_f64_host": (_int, [_i64, _i64, _i64, _vp, _vp, _dbl, _dbl, _dbl, _vp, _dbl, _dbl, _dbl, _vp]),
     "npb_adi_f64": (_int, [_i64, _i64, _vp]),
     "npb_adi_f64_host": (_int, [_i64, _i64, _vp]),
     "npb_jacobi2d_f64_host": (_int, [_i64, _i64, _i64, _vp, _vp]),

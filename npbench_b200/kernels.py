@@ -9,6 +9,8 @@ reference functions they mutate their array arguments and return None.
 Reference signatures: bench_info/{jacobi_2d,heat_3d,fdtd_2d,hdiff,vadv}.json
 "input_args"; implementations npbench/benchmarks/**/<bench>_numpy.py.
 """
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -133,3 +135,18 @@ def cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu):
     L = _lib.lib()
     fn = L.cavity_flow_f64 if _kind(u, v, p) == "device" else L.cavity_flow_f64_host
     fn(int(nx), int(ny), int(nt), int(nit), _p(u), _p(v), float(dt), float(dx), float(dy), _p(p), float(rho), float(nu))
+
+
+def channel_flow(nit, u, v, dt, dx, dy, p, rho, nu, F):
+    """channel_flow(nit, u, v, dt, dx, dy, p, rho, nu, F) -> stepcount -- channel_flow/channel_flow_numpy.py:74-170."""
+    if len(u.shape) != 2 or tuple(v.shape) != tuple(u.shape) or tuple(p.shape) != tuple(u.shape):
+        raise ValueError("u, v and p must be 2-D arrays of the same shape")
+    ny, nx = u.shape
+    if nx < 3 or ny < 3:
+        raise ValueError("nx and ny must be >= 3")
+    L = _lib.lib()
+    fn = L.channel_flow_f64 if _kind(u, v, p) == "device" else L.channel_flow_f64_host
+    steps = ctypes.c_int64(0)
+    fn(int(nit), nx, ny, _p(u), _p(v), float(dt), float(dx), float(dy), _p(p), float(rho), float(nu), float(F),
+       ctypes.addressof(steps))
+    return int(steps.value)

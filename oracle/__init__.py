@@ -51,6 +51,11 @@ def lib():
         L.npb_oracle_init_adi.argtypes = [_i64, _dp]
         L.npb_oracle_cavity_flow.argtypes = [_i64, _i64, _i64, _i64, _dp, _dp, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_double, _dp, ctypes.c_double, ctypes.c_double]
+        L.npb_oracle_channel_flow.argtypes = [_i64, _i64, _i64, _dp, _dp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                              _dp, ctypes.c_double, ctypes.c_double, ctypes.c_double, _i64]
+        L.npb_oracle_channel_flow.restype = _i64
+        L.npb_oracle_np_sum.argtypes = [_dp, _i64]
+        L.npb_oracle_np_sum.restype = ctypes.c_double
         _LIB = L
     return _LIB
 
@@ -132,7 +137,28 @@ def cavity_flow(nx, ny, nt, nit, u, v, dt, dx, dy, p, rho, nu):
                                  _ptr(p), float(rho), float(nu))
 
 
+def channel_flow(nit, u, v, dt, dx, dy, p, rho, nu, F, max_steps=10 ** 7):
+    """channel_flow/channel_flow_numpy.py:74-170; returns stepcount like the reference"""
+    ny, nx = u.shape
+    assert v.shape == u.shape and p.shape == u.shape and nx >= 3 and ny >= 3
+    return int(lib().npb_oracle_channel_flow(int(nit), nx, ny, _ptr(u), _ptr(v), float(dt), float(dx), float(dy), _ptr(p),
+                                             float(rho), float(nu), float(F), int(max_steps)))
+
+
+def np_sum(a):
+    """NumPy's pairwise summation of a contiguous float64 array (np.sum), restated"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return float(lib().npb_oracle_np_sum(_ptr(a), a.size))
+
+
 # -- initialisers (NPBench's `initialize` functions restated) ----------------
+
+def init_channel_flow(ny, nx):
+    """channel_flow/channel_flow.py -> u, v, p, dx, dy, dt"""
+    u = np.zeros((ny, nx)); v = np.zeros((ny, nx)); p = np.ones((ny, nx))
+    return u, v, p, 2 / (nx - 1), 2 / (ny - 1), .1 / ((nx - 1) * (ny - 1))
+
+
 
 def init_cavity_flow(ny, nx):
     """cavity_flow/cavity_flow.py:6-13 -> u, v, p, dx, dy, dt"""
@@ -231,6 +257,9 @@ PRESETS = {
     "cavity_flow": {"S": dict(ny=61, nx=61, nt=25, nit=5, rho=1.0, nu=0.1), "M": dict(ny=121, nx=121, nt=50, nit=10, rho=1.0, nu=0.1),
                     "L": dict(ny=201, nx=201, nt=100, nit=20, rho=1.0, nu=0.1),
                     "paper": dict(ny=101, nx=101, nt=700, nit=50, rho=1.0, nu=0.1)},
+    "channel_flow": {"S": dict(ny=61, nx=61, nit=5, rho=1.0, nu=0.1, F=1.0), "M": dict(ny=121, nx=121, nit=10, rho=1.0, nu=0.1, F=1.0),
+                     "L": dict(ny=201, nx=201, nit=20, rho=1.0, nu=0.1, F=1.0),
+                     "paper": dict(ny=101, nx=101, nit=50, rho=1.0, nu=0.1, F=1.0)},
     "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200),
             "L": dict(TSTEPS=50, N=500), "paper": dict(TSTEPS=100, N=200)},
 }

@@ -25,6 +25,8 @@ PRESETS = {  # bench_info/{jacobi_1d,seidel_2d}.json "parameters"
     "seidel_2d": {"S": dict(TSTEPS=8, N=50), "M": dict(TSTEPS=15, N=100), "L": dict(TSTEPS=40, N=200)},
     "adi": {"S": dict(TSTEPS=5, N=100), "M": dict(TSTEPS=20, N=200), "paper": dict(TSTEPS=100, N=200)},
     "cavity_flow": {"S": dict(ny=61, nx=61, nt=25, nit=5, rho=1.0, nu=0.1), "M": dict(ny=121, nx=121, nt=50, nit=10, rho=1.0, nu=0.1)},
+    "channel_flow": {"S": dict(ny=61, nx=61, nit=5, rho=1.0, nu=0.1, F=1.0), "M": dict(ny=121, nx=121, nit=10, rho=1.0, nu=0.1, F=1.0),
+                     "paper": dict(ny=101, nx=101, nit=50, rho=1.0, nu=0.1, F=1.0)},
 }
 
 
@@ -63,6 +65,14 @@ def main():
         c_kern(p["nx"], p["ny"], p["nt"], p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"])
         e["out"] = {"u": digest(u), "v": digest(v), "p": digest(pr)}
         pins["cavity_flow/" + preset] = e
+    h_init = ref("channel_flow", "channel_flow", "initialize")
+    h_kern = ref("channel_flow", "channel_flow_numpy", "channel_flow")
+    for preset, p in PRESETS["channel_flow"].items():
+        u, v, pr, dx, dy, dt = h_init(p["ny"], p["nx"])
+        e = {"in": {"u": digest(u), "v": digest(v), "p": digest(pr)}, "dx": dx, "dy": dy, "dt": dt}
+        e["stepcount"] = int(h_kern(p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"], p["F"]))
+        e["out"] = {"u": digest(u), "v": digest(v), "p": digest(pr)}
+        pins["channel_flow/" + preset] = e
     with open(os.path.join(HERE, "pins_next.json"), "w") as f:
         json.dump(pins, f, indent=1, sort_keys=True)
 
@@ -99,6 +109,17 @@ def main():
         i = dict(u_in=u.copy(), v_in=v.copy(), p_in=pr.copy())
         c_kern(nx, ny, nt, nit, u, v, dt, dx, dy, pr, 1.3, 0.07)
         put("cavity_flow.%d" % n, nx=nx, ny=ny, nt=nt, nit=nit, dt=dt, dx=dx, dy=dy, rho=1.3, nu=0.07, u_out=u, v_out=v, p_out=pr, **i)
+    # channel_flow cases (drawn last): the reference's own initial fields on small / rectangular grids with other
+    # nit, rho, nu, F, plus np.sum reference values for the pairwise-summation restatement
+    for n, (nx, ny, nit, rho, nu, F) in enumerate([(3, 3, 1, 1.0, 0.1, 1.0), (9, 7, 3, 1.0, 0.1, 1.0), (17, 12, 0, 1.0, 0.2, 0.5),
+                                                   (31, 21, 4, 1.3, 0.07, 1.0), (16, 33, 6, 0.9, 0.15, 2.0)]):
+        u, v, pr, dx, dy, dt = h_init(ny, nx)
+        sc = h_kern(nit, u, v, dt, dx, dy, pr, rho, nu, F)
+        put("channel_flow.%d" % n, nx=nx, ny=ny, nit=nit, dt=dt, dx=dx, dy=dy, rho=rho, nu=nu, F=F, stepcount=sc,
+            u_out=u, v_out=v, p_out=pr)
+    for n, size in enumerate([1, 7, 8, 9, 100, 128, 129, 1000, 3721, 10201, 14641, 40401]):
+        a = (rng.random(size) - 0.3) * 10.0 ** float(rng.integers(-3, 4))
+        put("npsum.%d" % n, a=a, s=np.float64(np.sum(a)))
     np.savez_compressed(os.path.join(HERE, "cases_next.npz"), **cases)
     print("pins:", len(pins) - 1, "cases arrays:", len(cases),
           "npz bytes:", os.path.getsize(os.path.join(HERE, "cases_next.npz")))

@@ -47,6 +47,10 @@ BENCH_INFO = {   # bench_info/<name>.json: relative_path, module_name, func_name
                         func_name="cavity_flow",
                         input_args=["nx", "ny", "nt", "nit", "u", "v", "dt", "dx", "dy", "p", "rho", "nu"],
                         array_args=["u", "v", "p"], output_args=["u", "v", "p"]),
+    "channel_flow": dict(short_name="chanflow", relative_path="channel_flow", module_name="channel_flow",
+                         func_name="channel_flow",
+                         input_args=["nit", "u", "v", "dt", "dx", "dy", "p", "rho", "nu", "F"],
+                         array_args=["u", "v", "p"], output_args=["u", "v", "p"]),
     "vadv": dict(short_name="vadv", relative_path="weather_stencils/vadv", module_name="vadv", func_name="vadv",
                  input_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens", "dtr_stage"],
                  array_args=["utens_stage", "u_stage", "wcon", "u_pos", "utens"], output_args=["utens_stage"]),

@@ -77,7 +77,32 @@ def test_oracle_cavity_flow_presets(pins_next, preset):
         assert sha(a) == pin["out"][name]["sha256"], name
 
 
+@pytest.mark.parametrize("preset", ["S", "M", "paper"])
+def test_oracle_channel_flow_presets(pins_next, preset):
+    p = oracle.PRESETS["channel_flow"][preset]; pin = pins_next["channel_flow/" + preset]
+    u, v, pr, dx, dy, dt = oracle.init_channel_flow(p["ny"], p["nx"])
+    oracle.set_threads(8)
+    try:
+        sc = oracle.channel_flow(p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"], p["F"])
+    finally:
+        oracle.set_threads(1)
+    assert sc == pin["stepcount"]
+    for name, a in (("u", u), ("v", v), ("p", pr)):
+        assert sha(a) == pin["out"][name]["sha256"], name
+
+
+def test_oracle_np_sum(cases_next):
+    for n, c in enumerate(cases_next["npsum"]):
+        assert oracle.np_sum(c["a"]) == float(c["s"]), "np.sum case %d (n=%d)" % (n, c["a"].size)
+
+
 def test_oracle_small_cases(cases_next):
+    for n, c in enumerate(cases_next["channel_flow"]):
+        u, v, pr, dx, dy, dt = oracle.init_channel_flow(int(c["ny"]), int(c["nx"]))
+        sc = oracle.channel_flow(int(c["nit"]), u, v, dt, dx, dy, pr, float(c["rho"]), float(c["nu"]), float(c["F"]))
+        assert sc == int(c["stepcount"]), "channel_flow.%d stepcount" % n
+        for name, a in (("u", u), ("v", v), ("p", pr)):
+            assert_bit_equal(a, c[name + "_out"], "channel_flow.%d %s" % (n, name))
     for n, c in enumerate(cases_next["cavity_flow"]):
         u, v, pr = c["u_in"].copy(), c["v_in"].copy(), c["p_in"].copy()
         oracle.cavity_flow(int(c["nx"]), int(c["ny"]), int(c["nt"]), int(c["nit"]), u, v, float(c["dt"]), float(c["dx"]),
@@ -200,6 +225,46 @@ def test_gpu_cavity_flow_presets(nb, pins_next, preset):
         oracle.cavity_flow(p["nx"], p["ny"], p["nt"], p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"])
     finally:
         oracle.set_threads(1)
+    assert_bit_equal(gu, u, "u"); assert_bit_equal(gv, v, "v"); assert_bit_equal(gp, pr, "p")
+
+
+def run_channel(nb, ny, nx, nit, rho, nu, F, host):
+    u, v, p, dx, dy, dt = oracle.init_channel_flow(ny, nx)
+    if host:
+        sc = nb.channel_flow(nit, u, v, dt, dx, dy, p, rho, nu, F)
+        return sc, u, v, p
+    d = [nb.DeviceArray.from_host(a) for a in (u, v, p)]
+    sc = nb.channel_flow(nit, d[0], d[1], dt, dx, dy, d[2], rho, nu, F)
+    return sc, d[0].to_host(), d[1].to_host(), d[2].to_host()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [False, True], ids=["device", "host"])
+def test_gpu_channel_flow_golden_cases(nb, cases_next, host):
+    for n, c in enumerate(cases_next["channel_flow"]):
+        sc, u, v, p = run_channel(nb, int(c["ny"]), int(c["nx"]), int(c["nit"]), float(c["rho"]), float(c["nu"]),
+                                  float(c["F"]), host)
+        assert sc == int(c["stepcount"]), "channel_flow.%d stepcount" % n
+        for name, g in (("u", u), ("v", v), ("p", p)):
+            assert_bit_equal(g, c[name + "_out"], "channel_flow.%d %s" % (n, name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["S", "M", "L", "paper"])
+def test_gpu_channel_flow_presets(nb, pins_next, preset):
+    p = oracle.PRESETS["channel_flow"][preset]
+    sc, gu, gv, gp = run_channel(nb, p["ny"], p["nx"], p["nit"], p["rho"], p["nu"], p["F"], host=False)
+    if "channel_flow/" + preset in pins_next:
+        pin = pins_next["channel_flow/" + preset]
+        assert sc == pin["stepcount"]
+        assert (sha(gu), sha(gv), sha(gp)) == tuple(pin["out"][k]["sha256"] for k in ("u", "v", "p"))
+    u, v, pr, dx, dy, dt = oracle.init_channel_flow(p["ny"], p["nx"])
+    oracle.set_threads(8)
+    try:
+        sc_ref = oracle.channel_flow(p["nit"], u, v, dt, dx, dy, pr, p["rho"], p["nu"], p["F"])
+    finally:
+        oracle.set_threads(1)
+    assert sc == sc_ref
     assert_bit_equal(gu, u, "u"); assert_bit_equal(gv, v, "v"); assert_bit_equal(gp, pr, "p")
 
 

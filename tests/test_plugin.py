@@ -36,6 +36,7 @@ def test_plugin_modules_have_the_numpy_signatures():
             "polybench/jacobi_1d/jacobi_1d_b200.py": ("kernel", ["TSTEPS", "A", "B"]),
             "polybench/seidel_2d/seidel_2d_b200.py": ("kernel", ["TSTEPS", "N", "A"]),
             "polybench/adi/adi_b200.py": ("kernel", ["TSTEPS", "N", "u"]),
+            "channel_flow/channel_flow_b200.py": ("channel_flow", ["nit", "u", "v", "dt", "dx", "dy", "p", "rho", "nu", "F"]),
             "cavity_flow/cavity_flow_b200.py": ("cavity_flow", ["nx", "ny", "nt", "nit", "u", "v", "dt", "dx", "dy", "p",
                                                                 "rho", "nu"]),
             "weather_stencils/hdiff/hdiff_b200.py": ("hdiff", ["in_field", "out_field", "coeff"]),
@@ -78,7 +79,7 @@ def test_b200_through_real_harness_fails_loudly_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d", "adi", "cavity_flow"])
+@pytest.mark.parametrize("bench", ["jacobi_2d", "heat_3d", "fdtd_2d", "hdiff", "vadv", "jacobi_1d", "seidel_2d", "adi", "cavity_flow", "channel_flow"])
 def test_plugin_end_to_end_with_standin_harness(bench):
     import harness_standin as hs
     infra = hs.install()
@@ -109,6 +110,11 @@ def test_plugin_end_to_end_with_standin_harness(bench):
                      nu=p["nu"])
         ref = lambda d: oracle.cavity_flow(d["nx"], d["ny"], d["nt"], d["nit"], d["u"], d["v"], d["dt"], d["dx"], d["dy"],
                                            d["p"], d["rho"], d["nu"])
+    elif bench == "channel_flow":
+        u, v, pr, dx, dy, dt = oracle.init_channel_flow(p["ny"], p["nx"])
+        bdata = dict(nit=p["nit"], u=u, v=v, dt=dt, dx=dx, dy=dy, p=pr, rho=p["rho"], nu=p["nu"], F=p["F"])
+        ref = lambda d: oracle.channel_flow(d["nit"], d["u"], d["v"], d["dt"], d["dx"], d["dy"], d["p"], d["rho"], d["nu"],
+                                            d["F"])
     elif bench == "adi":
         bdata = dict(TSTEPS=p["TSTEPS"], N=p["N"], u=oracle.init_adi(p["N"]))
         ref = lambda d: oracle.adi(d["TSTEPS"], d["N"], d["u"])
@@ -124,7 +130,10 @@ def test_plugin_end_to_end_with_standin_harness(bench):
     out, times = hs.execute(frm, b, impl, bdata, repeat=3)
     nout = len(b.info["output_args"])
     # adi returns its argument like the reference does (adi_numpy.py:54): returned values come first (test.py:39-50)
-    assert len(times) == 3 and len(out) == nout + (1 if bench == "adi" else 0)
+    # ... and channel_flow its step count (channel_flow_numpy.py:170)
+    assert len(times) == 3 and len(out) == nout + (1 if bench in ("adi", "channel_flow") else 0)
+    if bench == "channel_flow":
+        assert out[0] == 982                                   # reference step count at preset S (pins_next.json)
     got = [frm.copy_back_func()(a) for a in out[-nout:]]
     want = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in bdata.items()}
     ref(want)

@@ -20,6 +20,7 @@ PRESETS = {
     "seidel_2d": {"S": (8, 50), "M": (15, 100), "L": (40, 200), "paper": (100, 400)},
     "adi": {"S": (5, 100), "M": (20, 200), "L": (50, 500), "paper": (100, 200)},
     "cavity_flow": {"S": (61, 25, 5), "M": (121, 50, 10), "L": (201, 100, 20), "paper": (101, 700, 50)},
+    "channel_flow": {"S": (61, 5), "M": (121, 10), "L": (201, 20), "paper": (101, 50)},
 }
 
 
@@ -99,6 +100,19 @@ def main():
                         L.d2d(x.ptr, x0.ptr, n * n * 8)
                     nb.cavity_flow(n, n, nt, nit, a[0], a[1], dt, dx, dx, a[2], 1.0, 0.1)
                 units = nt * (nit + 2) * (n - 2) ** 2; bpu = 16
+            elif bench == "channel_flow":
+                n, nit = p
+                a0 = [nb.DeviceArray.from_host(x) for x in (np.zeros((n, n)), np.zeros((n, n)), np.ones((n, n)))]
+                a = [nb.DeviceArray((n, n)) for _ in range(3)]
+                dx = 2 / (n - 1); dt = .1 / ((n - 1) * (n - 1))
+                box = {}
+
+                def fn(a=a, a0=a0, n=n, nit=nit, dx=dx, dt=dt, box=box):
+                    for x, x0 in zip(a, a0):
+                        L.d2d(x.ptr, x0.ptr, n * n * 8)
+                    box["steps"] = nb.channel_flow(nit, a[0], a[1], dt, dx, dx, a[2], 1.0, 0.1, 1.0)
+                fn()
+                units = box["steps"] * (nit + 2) * n * (n - 2); bpu = 16
             elif bench == "hdiff":
                 I, J, K = p
                 a = [nb.DeviceArray.from_host(rng.random(s)) for s in ((I + 4, J + 4, K), (I, J, K), (I, J, K))]
