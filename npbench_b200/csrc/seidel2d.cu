@@ -21,6 +21,7 @@
 //
 // Arithmetic order as in oracle/stencil_oracle.c: npb_oracle_seidel2d; IEEE division; -fmad=false.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -118,12 +119,19 @@ seidel2d_dsmem_kernel(int tsteps, int n, int R, double *A) {
 }
 
 // 1 launched, 0 not applicable
-int try_dsmem(int64_t tsteps, int64_t n, double *A) {
-    const int csize = 8;                                         // portable cluster size
+int launch_dsmem(int csize, int64_t tsteps, int64_t n, double *A) {
     const int R = (int)((n + csize - 1) / csize);
     const size_t smem = (size_t)R * n * sizeof(double);
     if (smem + 1024 > npb::st().smem_optin || n < 3 * csize) return 0;
     static size_t configured = 0;
+    static bool nonportable = false;
+    if (csize > 8 && !nonportable) {
+        if (cudaFuncSetAttribute(seidel2d_dsmem_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        nonportable = true;
+    }
     if (smem > configured) {
         if (cudaFuncSetAttribute(seidel2d_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
@@ -144,6 +152,15 @@ int try_dsmem(int64_t tsteps, int64_t n, double *A) {
         return 0;
     }
     return 1;
+}
+
+// 1 launched, 0 not applicable.  16 CTAs per cluster (the B200 maximum, non-portable) when the work is large
+// enough to be compute bound on 8 SMs; 8 otherwise.
+int try_dsmem(int64_t tsteps, int64_t n, double *A) {
+    static int big = -1;
+    if (big < 0) { const char *e = getenv("NPB_SEIDEL_CLUSTER"); big = e ? atoi(e) : 16; }
+    if (big == 16 && (tsteps - 1) * (n - 2) >= 8LL * S2_THREADS && launch_dsmem(16, tsteps, n, A) == 1) return 1;
+    return launch_dsmem(8, tsteps, n, A);
 }
 
 int g_seidel_mode = 0;     // 0 dispatch (DSMEM kernel when the grid fits in one cluster), 1 L2 wavefront kernel
