@@ -27,8 +27,8 @@
 
 namespace {
 
-constexpr int S2_THREADS = 1024;
-constexpr int S2_SLOTS = 6;          // row tasks per thread kept decoded in registers (DSMEM kernel)
+constexpr int S2_THREADS = 512;
+constexpr int S2_SLOTS = 12;         // row tasks per thread kept decoded in registers (DSMEM kernel)
 
 __global__ void __launch_bounds__(S2_THREADS, 1)
 seidel2d_wavefront_kernel(int tsteps, int n, double *A) {
