@@ -106,16 +106,15 @@ hdiff_march_kernel(int I, int JK, int K, long long in_pitch,   // in_pitch = (J+
 // CTA streams whole input rows (and the matching coeff rows) into a ring of
 // shared-memory slots with cp.async.bulk (the TMA engine, 1-D bulk form),
 // completion tracked by mbarriers; 15 consumer warps take each row out of the
-// ring exactly once -- 5 x 16-byte shared loads per thread (columns q-2..q+2)
-// into a register window that carries the rows still needed -- so a slot is
+// ring exactly once -- 6 x 8-byte shared loads per thread (columns q-2..q+3 of its
+// two j-adjacent cells) into a register window that carries the rows still needed -- so a slot is
 // released the moment it has been read and all other slots are look-ahead
 // (up to 7 rows, ~140 KB in flight per SM).  Work units (i-block, j-tile) are dealt
 // round-robin so that concurrently running CTAs share their halos through L2.
 // ---------------------------------------------------------------------------
 namespace ring {
 
-constexpr int MAX_SLOTS = 8;
-constexpr int CONSUMERS = 480;               // 15 warps, two adjacent k per thread (512 threads => 128 regs each)
+constexpr int CONSUMERS = 480;               // 15 warps, two j-adjacent cells per thread (512 threads => 128 regs each)
 constexpr int THREADS = CONSUMERS + 32;      // + producer warp
 
 struct Params {
@@ -152,51 +151,47 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ double2 lap5v(double2 c, double2 ip, double2 im, double2 jp, double2 jm) {
-    return make_double2(lap5(c.x, ip.x, im.x, jp.x, jm.x), lap5(c.y, ip.y, im.y, jp.y, jm.y));
-}
-__device__ __forceinline__ double2 limitv(double2 a, double2 b, double2 hi, double2 lo) {
-    // limit(a - b, hi - lo) per component
-    return make_double2(limit(a.x - b.x, hi.x - lo.x), limit(a.y - b.y, hi.y - lo.y));
-}
-
-// One consumer step: row `r` of the current unit has landed in `row`; W is the static position of
-// that row in the 4-deep circular register windows (W == (r - i0) & 3 after 4x unrolling), so no
-// register is ever moved: C/L/Rr hold columns q, q-1, q+1, LL/RR columns q-2, q+2, indexed by row & 3.
+// One consumer step: row `r` of the current unit has landed in `row`; W is the static position of that row in
+// the 4-deep circular register windows (W == (r - i0) & 3 after 4x unrolling), so no register is ever moved.
+// A thread owns TWO j-ADJACENT output cells A = (q, k) and B = (q+1, k) and keeps the six input columns
+// q-2 .. q+3 (X[0..5]; X[2] = A, X[3] = B): the Laplacian of each of its cells is carried from row to row, so
+// lap(p, q+1) for A and lap(p, q-1) for B come for free, and the y-flux between A and B is computed once --
+// 4 Laplacians and 5 limiters per two cells instead of 6 and 6 (25 instead of 32 flops per cell; the consumer
+// warps were issue bound).  Same per-cell expressions in the same order, so the results are bit-identical.
 template <int W>
-__device__ __forceinline__ void consume_row(const Params &p, const double *row, int r, int i0, int j0, int e0,
-                                            bool active, double2 (&C)[4], double2 (&Lw)[4], double2 (&Rw)[4],
-                                            double2 (&LL)[4], double2 (&RR)[4], double2 &lap_c, double2 &flx_m,
-                                            unsigned long long *empty_bar, int lane) {
+__device__ __forceinline__ void consume_row(const Params &p, const double *row, int r, int i0, int j0, int ebase,
+                                            bool actA, bool actB, double (&X)[6][4], double &lapA, double &lapB,
+                                            double &flxmA, double &flxmB, unsigned long long *empty_bar, int lane) {
     const int K = p.K;
-    double2 cf = make_double2(0.0, 0.0);
-    if (active) {
-        const double *c = row + e0 + 2 * K;           // in[r, q, k] for this thread's (q, k) pair
-        C[W] = *reinterpret_cast<const double2 *>(c);
-        Lw[W] = *reinterpret_cast<const double2 *>(c - K);
-        Rw[W] = *reinterpret_cast<const double2 *>(c + K);
-        LL[W] = *reinterpret_cast<const double2 *>(c - 2 * K);
-        RR[W] = *reinterpret_cast<const double2 *>(c + 2 * K);
-        if (r - 4 >= i0) cf = *reinterpret_cast<const double2 *>(row + p.slot_in_elems + e0);
+    double cfA = 0.0, cfB = 0.0;
+    if (actA) {
+        const double *c = row + ebase + 2 * K;        // in[r, q, k]
+#pragma unroll
+        for (int d = 0; d < 6; ++d) X[d][W] = c[(d - 2) * K];
+        if (r - 4 >= i0) {
+            cfA = row[p.slot_in_elems + ebase];
+            if (actB) cfB = row[p.slot_in_elems + ebase + K];
+        }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar);            // this warp is done with the slot
     // rows: r -> W, r-1 -> W+3, r-2 (centre row p) -> W+2, r-3 -> W+1   (indices mod 4)
     constexpr int P2 = W, P1 = (W + 3) & 3, P0 = (W + 2) & 3, M1 = (W + 1) & 3;
-    const double2 lap_p = lap5v(C[P1], C[P2], C[P0], Rw[P1], Lw[P1]);      // lap(p+1, q)
-    const double2 lap_r = lap5v(Rw[P0], Rw[P1], Rw[M1], RR[P0], C[P0]);    // lap(p, q+1)
-    const double2 lap_l = lap5v(Lw[P0], Lw[P1], Lw[M1], C[P0], LL[P0]);    // lap(p, q-1)
-    const double2 flx_c = limitv(lap_p, lap_c, C[P1], C[P0]);
-    const double2 fly_c = limitv(lap_r, lap_c, Rw[P0], C[P0]);
-    const double2 fly_m = limitv(lap_c, lap_l, C[P0], Lw[P0]);
-    if (active && r - 4 >= i0) {
-        double2 res;
-        res.x = C[P0].x - cf.x * (((flx_c.x - flx_m.x) + fly_c.x) - fly_m.x);
-        res.y = C[P0].y - cf.y * (((flx_c.y - flx_m.y) + fly_c.y) - fly_m.y);
-        double2 *o = reinterpret_cast<double2 *>(p.out + ((long long)(r - 4) * p.J + j0) * K + e0);
-        __stcs(o, res);
+    const double lap_pA = lap5(X[2][P1], X[2][P2], X[2][P0], X[3][P1], X[1][P1]);     // lap(p+1, q)
+    const double lap_pB = lap5(X[3][P1], X[3][P2], X[3][P0], X[4][P1], X[2][P1]);     // lap(p+1, q+1)
+    const double lap_l = lap5(X[1][P0], X[1][P1], X[1][M1], X[2][P0], X[0][P0]);      // lap(p, q-1)
+    const double lap_r = lap5(X[4][P0], X[4][P1], X[4][M1], X[5][P0], X[3][P0]);      // lap(p, q+2)
+    const double flx_cA = limit(lap_pA - lapA, X[2][P1] - X[2][P0]);
+    const double flx_cB = limit(lap_pB - lapB, X[3][P1] - X[3][P0]);
+    const double fly_l = limit(lapA - lap_l, X[2][P0] - X[1][P0]);                    // between (p, q-1) and (p, q)
+    const double fly_ab = limit(lapB - lapA, X[3][P0] - X[2][P0]);                    // between A and B
+    const double fly_r = limit(lap_r - lapB, X[4][P0] - X[3][P0]);                    // between (p, q+1) and (p, q+2)
+    if (actA && r - 4 >= i0) {
+        double *o = p.out + ((long long)(r - 4) * p.J + j0) * K + ebase;
+        __stcs(o, X[2][P0] - cfA * (((flx_cA - flxmA) + fly_ab) - fly_l));
+        if (actB) __stcs(o + K, X[3][P0] - cfB * (((flx_cB - flxmB) + fly_r) - fly_ab));
     }
-    lap_c = lap_p; flx_m = flx_c;
+    lapA = lap_pA; lapB = lap_pB; flxmA = flx_cA; flxmB = flx_cB;
 }
 
 template <int NS>
@@ -245,24 +240,27 @@ hdiff_ring_kernel(Params p) {
     }
 
     // ---------------------------------- consumers ---------------------------------
-    const int e0 = 2 * tid;                       // first of the two adjacent flattened (j,k) elements
+    const int pj = tid / K, kk = tid - pj * K;    // pair of output columns (2*pj, 2*pj+1) of the tile, level kk
+    const int ebase = 2 * pj * K + kk;            // flattened (column, k) of cell A inside the tile's output row
     const int lane = tid & 31;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int ib = u / p.n_jtiles, jt = u - ib * p.n_jtiles;
         const int i0 = ib * p.RB, i1 = min(I, i0 + p.RB);
         const int j0 = jt * p.TJ, tjc = min(p.TJ, J - j0);
-        const bool active = e0 < tjc * K;
-        const double2 z = make_double2(0.0, 0.0);
-        double2 C[4] = {z, z, z, z}, Lw[4] = {z, z, z, z}, Rw[4] = {z, z, z, z}, LL[4] = {z, z, z, z},
-                RR[4] = {z, z, z, z};
-        double2 lap_c = z, flx_m = z;
+        const bool actA = 2 * pj < tjc, actB = 2 * pj + 1 < tjc;
+        double X[6][4];
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) X[d][q] = 0.0;
+        double lapA = 0.0, lapB = 0.0, flxmA = 0.0, flxmB = 0.0;
         const int r_end = i1 + 4;
 #define NPB_HD_STEP(WPOS)                                                                              \
         if (r < r_end) {                                                                               \
             const int slot = job & (NS - 1);                                                           \
             mbar_wait(&full_bar[slot], (job / NS) & 1u);                                               \
-            consume_row<WPOS>(p, ring_mem + (size_t)slot * p.slot_elems, r, i0, j0, e0, active, C, Lw, \
-                              Rw, LL, RR, lap_c, flx_m, &empty_bar[slot], lane);                       \
+            consume_row<WPOS>(p, ring_mem + (size_t)slot * p.slot_elems, r, i0, j0, ebase, actA, actB, \
+                              X, lapA, lapB, flxmA, flxmB, &empty_bar[slot], lane);                    \
             ++r; ++job;                                                                                \
         }
         for (int r = i0; r < r_end;) {
@@ -279,10 +277,10 @@ int g_hdiff_last = 0;        // 1 marching, 2 ring
 
 // Returns 1 if the ring kernel was launched, 0 if not applicable.
 int try_ring(int64_t I, int64_t J, int64_t K, const double *in, double *out, const double *coeff, bool force) {
-    if ((K & 1) || K > 2 * ring::CONSUMERS || K < 2) return 0;       // 16-byte aligned rows; one row tile per CTA
-    int TJ = (int)((2 * ring::CONSUMERS) / K);
-    if (TJ > J) TJ = (int)J;
-    if (TJ < 1) return 0;
+    if ((K & 1) || K > ring::CONSUMERS || K < 2) return 0;           // 16-byte aligned rows; one row tile per CTA
+    int TJ = 2 * (int)(ring::CONSUMERS / K);                       // column pairs x K threads <= CONSUMERS
+    if (TJ > J) TJ = (int)((J + 1) & ~1LL);
+    if (TJ < 2) return 0;
     const int n_jtiles = (int)((J + TJ - 1) / TJ);
     const int sms = npb::st().sm_count;
     if (!force && (long long)n_jtiles * I < 16LL * sms) return 0;     // too little work per SM
