@@ -775,6 +775,8 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     return 0;
 }
 
+#include "heat3d_march.cuh"
+
 bool g_use_graphs = true;
 int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 one-sweep resident kernel if eligible,
                        // 3 temporally blocked passes, 4 two-sweep resident kernel if eligible
@@ -824,6 +826,10 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
         size_t smem = 0;
         const int T = tb_pick_tile(n0, n1, n2, &smem);
         if (T > 0) { g_last_path = 3; return run_tb(T, smem, 2 * (tsteps - 1), n0, n1, n2, A, B); }
+    }
+    if (g_mode == 5 && tsteps >= 3 && march_eligible(n0, n1, n2)) {   // three sweeps per pass over HBM
+        g_last_path = 5;
+        return run_march(2 * (tsteps - 1), n0, n1, n2, A, B);
     }
     g_last_path = 2;
     // hundreds of short dependent launches: capture once, replay as one graph launch
