@@ -779,9 +779,10 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
 
 bool g_use_graphs = true;
 int g_mode = 0;        // 0 dispatch by size, 1 streaming only, 2 one-sweep resident kernel if eligible,
-                       // 3 temporally blocked passes, 4 two-sweep resident kernel if eligible
+                       // 3 temporally blocked passes, 4 two-sweep resident kernel if eligible,
+                       // 5 three-sweep marching passes (heat3d_march.cuh) whenever the shape allows
 int g_last_path = 0;   // 1 resident kernel (1 sweep/exchange), 2 one launch per sweep, 3 blocked passes,
-                       // 4 resident kernel (2 sweeps/exchange)
+                       // 4 resident kernel (2 sweeps/exchange), 5 three-sweep marching passes
 
 }  // namespace
 
@@ -827,7 +828,9 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
         const int T = tb_pick_tile(n0, n1, n2, &smem);
         if (T > 0) { g_last_path = 3; return run_tb(T, smem, 2 * (tsteps - 1), n0, n1, n2, A, B); }
     }
-    if (g_mode == 5 && tsteps >= 3 && march_eligible(n0, n1, n2)) {   // three sweeps per pass over HBM
+    // grids far beyond the L2 (measured crossover ~300^3): three sweeps per pass over HBM
+    const bool march_auto = (g_mode == 0) && n0 * n1 * n2 >= 40000000LL && n1 >= 128 && n2 >= 128;
+    if ((g_mode == 5 || march_auto) && tsteps >= 3 && march_eligible(n0, n1, n2)) {
         g_last_path = 5;
         return run_march(2 * (tsteps - 1), n0, n1, n2, A, B);
     }
