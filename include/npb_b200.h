@@ -104,6 +104,11 @@ int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, 
 /* kernel(TMAX, ex, ey, hz, _fict_): polybench/fdtd_2d/fdtd_2d_numpy.py:4-11. */
 int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz,
                    const double *fict);
+/* mode & 3: 0 = dispatch by size (grids of >= 4M cells: marching passes of up to four time steps,
+ * fdtd2d_march_kernel; else one launch per step), 1 = always one launch per step, 2 = marching
+ * passes at any size (TMAX >= 2); mode >> 8 = rows per chunk of the marching kernel (0 = automatic). */
+int npb_fdtd2d_set_mode(int mode);
+int npb_fdtd2d_last_path(void);          /* last call: 1 one launch per step, 2 marching passes */
 /* one fused time step on a row slab: local rows [0, nrows) are global rows
  * [row0, row0+nrows) of an nx_global-row grid; src fields -> dst fields
  * (out of place); `fict_t` is _fict_[t].  Rows whose stencil leaves the slab

@@ -77,7 +77,23 @@ int launch_step(const FdtdParams &p) {
     return 0;
 }
 
+#include "fdtd2d_march.cuh"
+
+int g_fd_mode = 0;      // 0 dispatch by size, 1 one launch per step, 2 marching passes whenever TMAX >= 2
+int g_fd_rc = 0;        // rows per chunk override for the marching kernel (0 = automatic)
+int g_fd_last = 0;      // 1 one launch per step, 2 marching passes
+
 }  // namespace
+
+// mode & 3: 0 = dispatch by size (marching passes of up to four steps for grids of >= 4M cells,
+// else one launch per step), 1 = always one launch per step, 2 = marching passes at any size;
+// mode >> 8: rows per chunk of the marching kernel (0 = automatic)
+extern "C" int npb_fdtd2d_set_mode(int mode) {
+    g_fd_mode = mode & 3;
+    g_fd_rc = mode >> 8;
+    return 0;
+}
+extern "C" int npb_fdtd2d_last_path(void) { return g_fd_last; }
 
 extern "C" int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
                                    const double *ex, const double *ey, const double *hz,
@@ -102,22 +118,39 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
     NPB_ARG(ws != nullptr, "npb_fdtd2d_f64", "cannot allocate the ping-pong workspace");
     double *u[3] = {ex, ey, hz};
     double *w[3] = {ws, ws + cells, ws + 2 * cells};
+    // passes of `ns` steps each; an even number of passes ends in the caller's arrays
+    const bool march = tmax >= 2 && nx >= 2 &&
+                       (g_fd_mode == 2 || (g_fd_mode == 0 && (int64_t)cells >= FM_AUTO_MIN_CELLS && ny >= 4 * FM_STRIP));
+    int64_t passes = tmax;
+    if (march) {
+        passes = (tmax + FM_MAX_STEPS - 1) / FM_MAX_STEPS;
+        if ((passes & 1) && tmax > passes) ++passes;
+    }
+    g_fd_last = march ? 2 : 1;
+    const int64_t base = tmax / passes, rem = tmax % passes;
     // TMAX short dependent launches: capture once per (extents, pointers), replay as one graph
     npb::GraphKey key;
     memset(&key, 0, sizeof(key));
-    key.kind = 2; key.dims[0] = tmax; key.dims[1] = nx; key.dims[2] = ny;
+    key.kind = 2; key.dims[0] = tmax; key.dims[1] = nx; key.dims[2] = ny; key.dims[3] = march ? 1 + g_fd_rc : 0;
     key.ptrs[0] = ex; key.ptrs[1] = ey; key.ptrs[2] = hz; key.ptrs[3] = fict; key.ptrs[4] = ws;
-    const bool use_graph = tmax > 8;
+    const bool use_graph = passes > 8;
     if (use_graph && npb::graph_replay(key)) return 0;
     const bool capturing = use_graph && npb::graph_begin();
     int rc = 0;
-    for (int64_t t = 0; t < tmax && !rc; ++t) {
-        double **s = (t & 1) ? w : u;
-        double **d = (t & 1) ? u : w;
-        FdtdParams p{nx, 0, nx, ny, 0, nx, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
-        rc = launch_step(p);
+    int64_t t = 0;
+    for (int64_t q = 0; q < passes && !rc; ++q) {
+        double **s = (q & 1) ? w : u;
+        double **d = (q & 1) ? u : w;
+        const int ns = (int)(base + (q < rem ? 1 : 0));
+        if (ns == 1) {
+            FdtdParams p{nx, 0, nx, ny, 0, nx, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, 0.0};
+            rc = launch_step(p);
+        } else {
+            rc = launch_march(ns, nx, ny, s[0], s[1], s[2], d[0], d[1], d[2], fict + t, g_fd_rc);
+        }
+        t += ns;
     }
-    if (!rc && (tmax & 1)) {   // result lives in the workspace: bring it home
+    if (!rc && (passes & 1)) {   // result lives in the workspace: bring it home
         for (int f = 0; f < 3 && !rc; ++f)
             if (cudaMemcpyAsync(u[f], w[f], cells * sizeof(double), cudaMemcpyDeviceToDevice, npb::st().stream) !=
                 cudaSuccess)

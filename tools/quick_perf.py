@@ -14,7 +14,7 @@ PRESETS = {
     "heat_3d": {"S": (25, 25), "M": (50, 40), "L": (100, 70), "paper": (500, 120), "big": (11, 640),
                 "n160": (41, 160), "n200": (41, 200), "n256": (21, 256), "n384": (11, 384), "n512": (11, 512), "n1024": (5, 1024)},
     "fdtd_2d": {"S": (20, 200, 220), "M": (60, 400, 450), "L": (150, 800, 900), "paper": (500, 1000, 1200),
-                "big": (10, 8192, 16384)},
+                "big": (10, 8192, 16384), "n2k": (20, 2048, 2048), "n4k": (20, 4096, 4096), "n3k": (20, 3072, 3072)},
     "hdiff": {"S": (64, 64, 60), "M": (128, 128, 160), "L": (384, 384, 160), "paper": (256, 256, 160)},
     "vadv": {"S": (60, 60, 40), "M": (112, 112, 80), "L": (180, 180, 160), "paper": (256, 256, 160)},
     "jacobi_1d": {"S": (800, 3200), "M": (3000, 12000), "L": (8500, 34000), "paper": (4000, 32000)},
@@ -47,6 +47,8 @@ def main():
     L = nb.lib()
     if os.environ.get('NPB_VADV_MODE'):
         L.vadv_set_mode(int(os.environ['NPB_VADV_MODE']))
+    if os.environ.get('NPB_FDTD_MODE'):
+        L.fdtd2d_set_mode(int(os.environ['NPB_FDTD_MODE']))
     if os.environ.get('NPB_HEAT_MODE'):
         L.heat3d_set_mode(int(os.environ['NPB_HEAT_MODE']))
     rng = np.random.default_rng(0)
