@@ -35,6 +35,7 @@ struct FmParams {
     long long nx, ny;
     long long nstrips;
     int rc;                    // output rows per chunk
+    int pfd;                   // L2 prefetch distance in rows (0 = off)
     const double *ex, *ey, *hz;
     double *exo, *eyo, *hzo;
     const double *fict;        // _fict_[t0 ...]
@@ -116,6 +117,12 @@ fdtd2d_march_kernel(FmParams p) {
         double ex_o[FM_COLS], ey_o[FM_COLS], hz_o[FM_COLS];
 #pragma unroll
         for (int m = 0; m < FM_COLS; ++m) { ex_o[m] = nex[m]; ey_o[m] = ney[m]; hz_o[m] = nhz[m]; }
+        if (p.pfd > 0 && full && r + p.pfd <= r_load_last) {   // pull a row further ahead into L2 (no registers held)
+            const long long a = src + (long long)p.pfd * ny;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ex + a));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ey + a));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.hz + a));
+        }
         if (r + 1 <= r_load_last) {                      // prefetch the next source row
             src += ny;
             fm_load_row<VEC>(p.ex + src, ny, col0, full, nex);
@@ -184,7 +191,9 @@ int launch_march(int ns, int64_t nx, int64_t ny, const double *ex, const double 
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("fdtd2d", "grid too large");
     const uintptr_t bits = (uintptr_t)ex | (uintptr_t)ey | (uintptr_t)hz | (uintptr_t)exo | (uintptr_t)eyo | (uintptr_t)hzo;
     const bool vec = (ny % 2 == 0) && (bits % 16 == 0);
-    FmParams p{nx, ny, nstrips, (int)rc, ex, ey, hz, exo, eyo, hzo, fict_t};
+    // measured at 8192 x 16384: 2.94 ms without, 2.71 ms at distance 2..4, 2.86 ms at 8
+    static const int pfd = getenv("NPB_FDTD_PFD") ? atoi(getenv("NPB_FDTD_PFD")) : 3;
+    FmParams p{nx, ny, nstrips, (int)rc, pfd, ex, ey, hz, exo, eyo, hzo, fict_t};
     dim3 grid((unsigned)blocks_x, (unsigned)chunks);
     switch (ns) {
         case 2: return launch_march_ns<2>(p, grid, vec);
