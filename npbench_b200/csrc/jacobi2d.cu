@@ -358,7 +358,8 @@ int try_resident(int64_t nsweeps, int64_t ni, int64_t nj, double *A, double *B) 
 }
 
 int g_jacobi_mode = 0;      // 0/1 blocked passes (default: faster measured), 2 resident kernel when the grid fits on chip
-int g_jacobi_last = 0;      // 1 resident, 2 blocked passes
+int g_jacobi_last = 0;      // 1 resident, 2 blocked passes, 3 marching passes
+int g_jacobi_rc = 0;        // rows per chunk override for the marching kernel
 
 template <class T>
 int launch_block_t(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, int64_t tr_lo,
@@ -405,7 +406,13 @@ int launch_block(int tile, int nsteps, int64_t ni, int64_t nj, const double *src
 
 // 0/1: temporally blocked passes (default; measured faster at S/M/L);
 // 2: on-chip resident kernel when the grid is eligible (opt-in), blocked passes otherwise
-extern "C" int npb_jacobi2d_set_mode(int mode) { g_jacobi_mode = mode; return 0; }
+#include "jacobi2d_march.cuh"
+
+constexpr long long JM_AUTO_MIN_CELLS = 2000000;   // default dispatch: grids at least this large march
+
+// mode & 7: 0 dispatch by size, 1 blocked shared-memory passes, 2 resident kernel when the grid fits,
+// 3 marching passes at any size; mode >> 8: rows per chunk of the marching kernel (0 = automatic)
+extern "C" int npb_jacobi2d_set_mode(int mode) { g_jacobi_mode = mode & 7; g_jacobi_rc = mode >> 8; return 0; }
 extern "C" int npb_jacobi2d_last_path(void) { return g_jacobi_last; }
 
 extern "C" int npb_jacobi2d_tile_rows(void) { return TileBig::TI; }
@@ -429,7 +436,9 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
     // B keeps state S-1 and A gets state S; the S-1 sweeps before it are split
     // into an ODD number of ODD-sized blocked passes (A->B, B->A, ..., A->B).
     if (g_jacobi_mode == 2 && try_resident(2 * (tsteps - 1), ni, nj, A, B) == 1) { g_jacobi_last = 1; return 0; }
-    g_jacobi_last = 2;
+    const bool march = (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP)) &&
+                       tsteps >= 3 && nj >= 8;
+    g_jacobi_last = march ? 3 : 2;
     const int64_t M = 2 * (tsteps - 1) - 1;
     int64_t n = (M + NPB_JACOBI2D_MAX_BLOCK - 1) / NPB_JACOBI2D_MAX_BLOCK;
     if ((n & 1) == 0) ++n;
@@ -439,7 +448,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
     // many short dependent passes on small grids: capture once, replay as one graph launch
     npb::GraphKey key;
     memset(&key, 0, sizeof(key));
-    key.kind = 3; key.dims[0] = tsteps; key.dims[1] = ni; key.dims[2] = nj;
+    key.kind = 3; key.dims[0] = tsteps; key.dims[1] = ni; key.dims[2] = nj; key.dims[3] = march ? 1 + g_jacobi_rc : 0;
     key.ptrs[0] = A; key.ptrs[1] = B;
     const bool use_graph = (n >= 8) && ni * nj <= (1LL << 24);
     if (use_graph && npb::graph_replay(key)) return 0;
@@ -451,7 +460,9 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
         int64_t take = (extra_pairs + left - 1) / left;   // spread evenly
         if (take > cap) take = cap;
         extra_pairs -= take;
-        rc = launch_block(tile, (int)(1 + 2 * take), ni, nj, src, dst, 0, -1);
+        const int ns = (int)(1 + 2 * take);
+        if (march && ns >= 3) rc = launch_jm(ns, ni, nj, src, dst, g_jacobi_rc);
+        else rc = launch_block(tile, ns, ni, nj, src, dst, 0, -1);
         double *t = src; src = dst; dst = t;
     }
     // now src == B (state S-1), dst == A

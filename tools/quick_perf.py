@@ -47,6 +47,8 @@ def main():
     L = nb.lib()
     if os.environ.get('NPB_VADV_MODE'):
         L.vadv_set_mode(int(os.environ['NPB_VADV_MODE']))
+    if os.environ.get('NPB_J2_MODE'):
+        L.jacobi2d_set_mode(int(os.environ['NPB_J2_MODE']))
     if os.environ.get('NPB_FDTD_MODE'):
         L.fdtd2d_set_mode(int(os.environ['NPB_FDTD_MODE']))
     if os.environ.get('NPB_HEAT_MODE'):
