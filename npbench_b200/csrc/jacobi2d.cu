@@ -408,7 +408,7 @@ int launch_block(int tile, int nsteps, int64_t ni, int64_t nj, const double *src
 // 2: on-chip resident kernel when the grid is eligible (opt-in), blocked passes otherwise
 #include "jacobi2d_march.cuh"
 
-constexpr long long JM_AUTO_MIN_CELLS = 2000000;   // default dispatch: grids at least this large march
+constexpr long long JM_AUTO_MIN_CELLS = 14000000;  // default dispatch: measured 2800^2 0.77x, 4096^2 1.2x, 8192^2 1.8x, 16384^2 2.0x
 
 // mode & 7: 0 dispatch by size, 1 blocked shared-memory passes, 2 resident kernel when the grid fits,
 // 3 marching passes at any size; mode >> 8: rows per chunk of the marching kernel (0 = automatic)
@@ -440,10 +440,12 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
                        tsteps >= 3 && nj >= 8;
     g_jacobi_last = march ? 3 : 2;
     const int64_t M = 2 * (tsteps - 1) - 1;
-    int64_t n = (M + NPB_JACOBI2D_MAX_BLOCK - 1) / NPB_JACOBI2D_MAX_BLOCK;
+    static const int march_max = getenv("NPB_J2_MAXNS") ? atoi(getenv("NPB_J2_MAXNS")) : 7;
+    const int64_t max_block = march ? (march_max >= 7 ? 7 : march_max >= 5 ? 5 : 3) : NPB_JACOBI2D_MAX_BLOCK;
+    int64_t n = (M + max_block - 1) / max_block;
     if ((n & 1) == 0) ++n;
     int64_t extra_pairs = (M - n) / 2;            // distribute in units of 2 sweeps
-    const int64_t cap = (NPB_JACOBI2D_MAX_BLOCK - 1) / 2;
+    const int64_t cap = (max_block - 1) / 2;
     const int tile = pick_tile(ni, nj);
     // many short dependent passes on small grids: capture once, replay as one graph launch
     npb::GraphKey key;

@@ -103,7 +103,7 @@ __device__ __forceinline__ void jm_sweeps(double (&P)[NS][2][JM_COLS], double (&
 }
 
 template <int NS, bool VEC>
-__global__ void __launch_bounds__(JM_WARPS * 32)
+__global__ void __launch_bounds__(JM_WARPS * 32, (NS <= 5) ? 3 : 2)
 jacobi2d_march_kernel(JmParams p) {
     static_assert(NS & 1, "a pass must go src -> dst");
     constexpr int HL = jm_halo_lanes(NS);

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import npbench_b200 as nb
 
 PRESETS = {
-    "jacobi_2d": {"S": (50, 150), "M": (80, 350), "L": (200, 700), "paper": (1000, 2800), "big": (21, 16384)},
+    "jacobi_2d": {"S": (50, 150), "M": (80, 350), "L": (200, 700), "paper": (1000, 2800), "big": (21, 16384), "n4k": (41, 4096), "n6k": (41, 6144), "n8k": (21, 8192)},
     "heat_3d": {"S": (25, 25), "M": (50, 40), "L": (100, 70), "paper": (500, 120), "big": (11, 640),
                 "n160": (41, 160), "n200": (41, 200), "n256": (21, 256), "n384": (11, 384), "n512": (11, 512), "n1024": (5, 1024)},
     "fdtd_2d": {"S": (20, 200, 220), "M": (60, 400, 450), "L": (150, 800, 900), "paper": (500, 1000, 1200),
