@@ -425,6 +425,16 @@ extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const 
     NPB_ARG(ni >= 0 && nj >= 0, "npb_jacobi2d_block_f64", "negative extent");
     NPB_ARG(nj - 2 < (int64_t)TileBig::TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
     if (ni < 3 || nj < 3) return 0;   // no interior
+    // big slabs: the same rows by marching passes (tile rows -> interior rows [1 + lo*TI, 1 + hi*TI))
+    if (nsteps >= 3 && nj >= 8 &&
+        (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP))) {
+        const int64_t tiles_i = (ni - 2 + TileBig::TI - 1) / TileBig::TI;
+        if (tile_row_hi < 0 || tile_row_hi > tiles_i) tile_row_hi = tiles_i;
+        if (tile_row_lo < 0) tile_row_lo = 0;
+        const int64_t row_lo = 1 + tile_row_lo * TileBig::TI;
+        const int64_t row_hi = (tile_row_hi >= tiles_i) ? ni - 1 : 1 + tile_row_hi * TileBig::TI;
+        return launch_jm(nsteps, ni, nj, src, dst, g_jacobi_rc, row_lo, row_hi);
+    }
     return launch_block(0, nsteps, ni, nj, src, dst, tile_row_lo, tile_row_hi);   // the sharded driver's big tile
 }
 

@@ -31,6 +31,7 @@ __host__ __device__ constexpr int jm_out_cols(int ns) { return JM_STRIP - 2 * JM
 struct JmParams {
     long long ni, nj;
     long long nstrips;
+    long long row_lo, row_hi;  // rows [row_lo, row_hi) are written by this launch (the sharded driver's ranges)
     int rc;                    // output rows per chunk
     int pfd;                   // L2 prefetch distance in rows (0 = off)
     const double *src;
@@ -115,8 +116,8 @@ jacobi2d_march_kernel(JmParams p) {
     const long long col0 = strip_c0 + JM_COLS * lane;
     const bool full = col0 >= 0 && col0 + JM_COLS <= nj;
     const bool edge_strip = strip_c0 <= 0 || strip_c0 + JM_STRIP >= nj;       // holds column 0 or nj-1 (warp-uniform)
-    const long long r0 = (long long)blockIdx.y * p.rc;
-    const long long r1 = (r0 + p.rc < ni) ? r0 + p.rc : ni;                   // rows [r0, r1) of the last state
+    const long long r0 = p.row_lo + (long long)blockIdx.y * p.rc;
+    const long long r1 = (r0 + p.rc < p.row_hi) ? r0 + p.rc : p.row_hi;       // rows [r0, r1) of the last state
     const long long r_first = (r0 - NS > 0) ? r0 - NS : 0;
     const long long r_last = r1 - 1 + NS;                                     // rows >= ni are virtual (flush)
     const long long r_load_last = (r_last < ni - 1) ? r_last : ni - 1;
@@ -227,20 +228,25 @@ int launch_jm_ns(const JmParams &p, dim3 grid, bool vec) {
 }
 
 // one pass: ns (3, 5 or 7) sweeps src -> dst
-int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, int rc_override) {
+int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, int rc_override, int64_t row_lo = 0,
+              int64_t row_hi = -1) {
+    if (row_hi < 0 || row_hi > ni) row_hi = ni;
+    if (row_lo < 0) row_lo = 0;
+    if (row_lo >= row_hi) return 0;
+    const long long rows = row_hi - row_lo;
     const long long out_cols = jm_out_cols(ns);
     const long long nstrips = (nj + out_cols - 1) / out_cols;
     const long long blocks_x = (nstrips + JM_WARPS - 1) / JM_WARPS;
     long long chunks = (48LL * npb::st().sm_count + nstrips - 1) / nstrips;
-    long long rc = (ni + chunks - 1) / chunks;
+    long long rc = (rows + chunks - 1) / chunks;
     if (rc < 64) rc = 64;
     if (rc_override > 0) rc = rc_override;
-    if (rc > ni) rc = ni;
-    chunks = (ni + rc - 1) / rc;
+    if (rc > rows) rc = rows;
+    chunks = (rows + rc - 1) / rc;
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("jacobi2d", "grid too large");
     const bool vec = (nj % 2 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0);
     static const int pfd = getenv("NPB_J2_PFD") ? atoi(getenv("NPB_J2_PFD")) : 3;
-    JmParams p{ni, nj, nstrips, (int)rc, pfd, src, dst};
+    JmParams p{ni, nj, nstrips, row_lo, row_hi, (int)rc, pfd, src, dst};
     dim3 grid((unsigned)blocks_x, (unsigned)chunks);
     switch (ns) {
         case 3: return launch_jm_ns<3>(p, grid, vec);
