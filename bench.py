@@ -583,7 +583,7 @@ def multi_gpu(args, world, rank, local_rank):
     torch.cuda.empty_cache()
     suite = multi_gpu_suite(args, world, rank, eng, D, torch, dist, peak) if not args.no_suite else None
 
-    # dominant kernel: the blocked jacobi pass (7 sweeps fused): 16 B x cells x sweeps per launch
+    # dominant kernel: the multi-sweep jacobi pass (up to 7 sweeps fused): 16 B x cells x sweeps per launch
     per_launch_sweeps = 2 * (WEAK_TSTEPS - 1) / max(1, len(D.jacobi_plan(2 * (WEAK_TSTEPS - 1))))
     achieved = value * 16.0 / world
     clocks = clk.summary()
@@ -597,7 +597,8 @@ def multi_gpu(args, world, rank, local_rank):
                                        "overlapped with interior tiles" % (n_rows, WEAK_COLS, WEAK_TSTEPS, world),
                            "l2": "inputs (13.4 GB per GPU) far larger than L2; no flush needed",
                            "timing": "CUDA events per step, barrier + synchronize before each, max over ranks"},
-                "roofline": {"bound": "hbm", "kernel": "jacobi2d blocked pass (csrc/jacobi2d.cu)",
+                "roofline": {"bound": "hbm", "kernel": "jacobi2d_march_kernel: 3/5/7 sweeps per pass in registers over the slab's row ranges "
+                                       "(csrc/jacobi2d_march.cuh, reached through npb_jacobi2d_block_f64)",
                              "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
                              "note": "per GPU, algorithmic 16 B per cell update; ~%.1f sweeps fused per launch so DRAM "

@@ -41,6 +41,19 @@ def main():
     ok["jacobi_2d"] = bool(np.array_equal(slab.owned(lA).cpu().numpy(), A[slab.lo:slab.hi]) and
                            np.array_equal(slab.owned(lB).cpu().numpy(), B[slab.lo:slab.hi]))
 
+    # the same grid with the block passes served by the marching kernel (what big slabs get by default)
+    A, B = rng.random((ni, nj)), rng.random((ni, nj))
+    lA, lB = dev(A, slab), dev(B, slab)
+    eng.lib.jacobi2d_set_mode(3)
+    try:
+        D.jacobi_2d_sharded(eng, slab, ts, lA, lB)
+        eng.synchronize()
+    finally:
+        eng.lib.jacobi2d_set_mode(0)
+    oracle.jacobi_2d(ts, A, B)
+    ok["jacobi_2d_march"] = bool(np.array_equal(slab.owned(lA).cpu().numpy(), A[slab.lo:slab.hi]) and
+                                 np.array_equal(slab.owned(lB).cpu().numpy(), B[slab.lo:slab.hi]))
+
     shape, ts, H = (24 * world + 5, 40, 50), 8, 4
     A, B = rng.random(shape), rng.random(shape)
     slab = D.Slab(shape[0], world, rank, H)
