@@ -103,6 +103,37 @@ __device__ __forceinline__ void jm_sweeps(double (&P)[NS][2][JM_COLS], double (&
     }
 }
 
+// one check-free sweep s of one row: P[s][U] (row q-2) is overwritten with the incoming row c, c becomes row q-1 of
+// state s+1
+template <int NS, int U>
+__device__ __forceinline__ void jm_sweep_fast(double (&P)[NS][2][JM_COLS], double (&c)[JM_COLS], const int s) {
+    const double left_lane = __shfl_up_sync(0xffffffffu, P[s][U ^ 1][JM_COLS - 1], 1);
+    const double right_lane = __shfl_down_sync(0xffffffffu, P[s][U ^ 1][0], 1);
+    double out[JM_COLS];
+#pragma unroll
+    for (int m = 0; m < JM_COLS; ++m) {
+        const double left = m ? P[s][U ^ 1][m - 1] : left_lane;
+        const double right = (m < JM_COLS - 1) ? P[s][U ^ 1][m + 1] : right_lane;
+        out[m] = 0.2 * ((((P[s][U ^ 1][m] + left) + right) + c[m]) + P[s][U][m]);   // jacobi_2d_numpy.py:7-10
+    }
+#pragma unroll
+    for (int m = 0; m < JM_COLS; ++m) { P[s][U][m] = c[m]; c[m] = out[m]; }
+}
+
+// Two consecutive rows, skewed by one sweep: sweep t of row r and sweep t-1 of row r+1 touch different P[s] and
+// different rows, so their FP64 chains are independent and interleave (eight chains per lane instead of four).
+template <int NS>
+__device__ __forceinline__ void jm_sweeps_pair(double (&P)[NS][2][JM_COLS], double (&c0)[JM_COLS],
+                                               double (&c1)[JM_COLS]) {
+    jm_sweep_fast<NS, 0>(P, c0, 0);
+#pragma unroll
+    for (int t = 1; t < NS; ++t) {
+        jm_sweep_fast<NS, 0>(P, c0, t);
+        jm_sweep_fast<NS, 1>(P, c1, t - 1);
+    }
+    jm_sweep_fast<NS, 1>(P, c1, NS - 1);
+}
+
 template <int NS, bool VEC>
 __global__ void __launch_bounds__(JM_WARPS * 32, (NS <= 5) ? 3 : 2)
 jacobi2d_march_kernel(JmParams p) {
@@ -212,9 +243,48 @@ jacobi2d_march_kernel(JmParams p) {
         }
         dst_off += nj;
     };
+    auto store_row = [&](const double (&c)[JM_COLS], const long long q_out) {
+        if (any_wr && q_out >= r0 && q_out < r1 && q_out >= 1 && q_out <= ni - 2) {
+            double *g = p.dst + dst_off;
+            if (vec_wr) {
+                reinterpret_cast<double2 *>(g)[0] = make_double2(c[0], c[1]);
+                reinterpret_cast<double2 *>(g)[1] = make_double2(c[2], c[3]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < JM_COLS; ++m)
+                    if (wr[m]) g[m] = c[m];
+            }
+        }
+        dst_off += nj;
+    };
+    // two rows at once when neither can complete a border row and the strip holds no border column
+    auto row_pair = [&](const long long r) {
+        double c0[JM_COLS], c1[JM_COLS];
+#pragma unroll
+        for (int m = 0; m < JM_COLS; ++m) { c0[m] = nxt[0][m]; c1[m] = nxt[1][m]; }
+        if (p.pfd > 0 && full && r + 1 + JM_PF + p.pfd <= r_load_last) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src + src_off + (long long)(1 + p.pfd) * nj));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.src + src_off + (long long)(2 + p.pfd) * nj));
+        }
+        if (r + JM_PF <= r_load_last) {
+            src_off += nj;
+            jm_load_row<VEC>(p.src + src_off, nj, col0, full, nxt[0]);
+        }
+        if (r + 1 + JM_PF <= r_load_last) {
+            src_off += nj;
+            jm_load_row<VEC>(p.src + src_off, nj, col0, full, nxt[1]);
+        }
+        jm_sweeps_pair<NS>(P, c0, c1);
+        store_row(c0, r - NS);
+        store_row(c1, r + 1 - NS);
+    };
     for (long long rb = r_first; rb <= r_last; rb += JM_PF) {
-        row_step(rb, std::integral_constant<int, 0>{});
-        if (rb + 1 <= r_last) row_step(rb + 1, std::integral_constant<int, 1>{});
+        if (!edge_strip && rb > NS && rb + 1 < ni - 1 && rb + 1 <= r_last) {
+            row_pair(rb);
+        } else {
+            row_step(rb, std::integral_constant<int, 0>{});
+            if (rb + 1 <= r_last) row_step(rb + 1, std::integral_constant<int, 1>{});
+        }
     }
 }
 
