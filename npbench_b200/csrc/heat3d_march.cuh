@@ -25,8 +25,11 @@ constexpr int HM_RJ = HM_TJ + 6, HM_RK = HM_TK + 6;   // region = tile + 3-deep 
 constexpr int HM_THREADS = 256;
 constexpr int HM_CELLS = HM_RJ * HM_RK;          // 1536
 constexpr int HM_CPT = HM_CELLS / HM_THREADS;    // 6 consecutive rows of one column per thread
-constexpr int HM_PAD = HM_RK;                    // one spare row either side: edge cells read in bounds
-constexpr size_t HM_SMEM = (size_t)(6 * HM_CELLS + 2 * HM_PAD) * sizeof(double);
+constexpr int HM_PAD = HM_RK;                    // one spare row above and below EVERY plane: the garbage cells of
+                                                 // region rows 0 / 23 read there, never in a plane another thread
+                                                 // is writing in the same plane step (racecheck-clean)
+constexpr int HM_PLANE = HM_CELLS + 2 * HM_PAD;  // shared stride between planes
+constexpr size_t HM_SMEM = (size_t)(6 * HM_PLANE) * sizeof(double);
 static_assert(HM_RK == 64 && HM_CPT * (HM_THREADS / HM_RK) == HM_RJ, "thread <-> cell mapping");
 
 struct HmParams {
@@ -106,12 +109,12 @@ __device__ __forceinline__ void hm_march(const HmParams &p, double *S, int tj, i
             for (int q = 0; q < HM_CPT; ++q) nb[q] = 0.0;
         }
         const int par = step & 1;
-        double *S0w = S + par * HM_CELLS + c0;                 // plane step   (holds plane step-2)
-        const double *S0r = S + (par ^ 1) * HM_CELLS + c0;     // plane step-1
-        double *S1w = S + (2 + (par ^ 1)) * HM_CELLS + c0;     // plane step-1 (holds plane step-3)
-        const double *S1r = S + (2 + par) * HM_CELLS + c0;     // plane step-2
-        double *S2w = S + (4 + par) * HM_CELLS + c0;           // plane step-2 (holds plane step-4)
-        const double *S2r = S + (4 + (par ^ 1)) * HM_CELLS + c0;   // plane step-3
+        double *S0w = S + par * HM_PLANE + c0;                 // plane step   (holds plane step-2)
+        const double *S0r = S + (par ^ 1) * HM_PLANE + c0;     // plane step-1
+        double *S1w = S + (2 + (par ^ 1)) * HM_PLANE + c0;     // plane step-1 (holds plane step-3)
+        const double *S1r = S + (2 + par) * HM_PLANE + c0;     // plane step-2
+        double *S2w = S + (4 + par) * HM_PLANE + c0;           // plane step-2 (holds plane step-4)
+        const double *S2r = S + (4 + (par ^ 1)) * HM_PLANE + c0;   // plane step-3
         const int p1 = step - 1, p2 = step - 2, p3 = step - 3;
         const bool bp1 = (p1 == 0 || p1 == n0 - 1), bp2 = (p2 == 0 || p2 == n0 - 1);
         const bool st3 = (p3 >= ia && p3 < ib);
