@@ -112,6 +112,9 @@ int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
  * passes at any size (TMAX >= 2); mode >> 8 = rows per chunk of the marching kernel (0 = automatic). */
 int npb_fdtd2d_set_mode(int mode);
 int npb_fdtd2d_last_path(void);          /* last call: 1 one launch per step, 2 marching passes */
+/* host logic only: the steps-per-pass plan of npb_fdtd2d_f64 (march != 0: up to five steps per pass, an even
+ * number of passes when TMAX allows); writes min(passes, cap) entries, returns the number of passes */
+int npb_fdtd2d_pass_plan(int64_t tmax, int march, int32_t *steps, int cap);
 /* one fused time step on a row slab: local rows [0, nrows) are global rows
  * [row0, row0+nrows) of an nx_global-row grid; src fields -> dst fields
  * (out of place); `fict_t` is _fict_[t].  Rows whose stencil leaves the slab

@@ -79,6 +79,20 @@ int launch_step(const FdtdParams &p) {
 
 #include "fdtd2d_march.cuh"
 
+// Passes of the time loop.  Marching: up to FM_MAX_STEPS steps per pass, and an even number of passes whenever
+// tmax allows it, so that the result ends in the caller's arrays without a copy; the steps are spread evenly
+// (the first `rem` passes take base + 1).  Otherwise one step per pass.
+void fdtd_plan(int64_t tmax, bool march, int64_t *passes, int64_t *base, int64_t *rem) {
+    int64_t n = tmax;
+    if (march) {
+        n = (tmax + FM_MAX_STEPS - 1) / FM_MAX_STEPS;
+        if ((n & 1) && tmax > n) ++n;
+    }
+    *passes = n;
+    *base = n ? tmax / n : 0;
+    *rem = n ? tmax % n : 0;
+}
+
 int g_fd_mode = 0;      // 0 dispatch by size, 1 one launch per step, 2 marching passes whenever TMAX >= 2
 int g_fd_rc = 0;        // rows per chunk override for the marching kernel (0 = automatic)
 int g_fd_last = 0;      // 1 one launch per step, 2 marching passes
@@ -94,6 +108,15 @@ extern "C" int npb_fdtd2d_set_mode(int mode) {
     return 0;
 }
 extern "C" int npb_fdtd2d_last_path(void) { return g_fd_last; }
+
+// host logic only (no device work): the pass plan npb_fdtd2d_f64 uses; writes min(passes, cap) entries
+extern "C" int npb_fdtd2d_pass_plan(int64_t tmax, int march, int32_t *steps, int cap) {
+    if (tmax <= 0) return 0;
+    int64_t passes, base, rem;
+    fdtd_plan(tmax, march != 0 && tmax >= 2, &passes, &base, &rem);
+    for (int64_t q = 0; q < passes && q < cap; ++q) steps[q] = (int32_t)(base + (q < rem ? 1 : 0));
+    return (int)passes;
+}
 
 extern "C" int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
                                    const double *ex, const double *ey, const double *hz,
@@ -121,13 +144,9 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
     // passes of `ns` steps each; an even number of passes ends in the caller's arrays
     const bool march = tmax >= 2 && nx >= 2 &&
                        (g_fd_mode == 2 || (g_fd_mode == 0 && (int64_t)cells >= FM_AUTO_MIN_CELLS && ny >= 4 * FM_STRIP));
-    int64_t passes = tmax;
-    if (march) {
-        passes = (tmax + FM_MAX_STEPS - 1) / FM_MAX_STEPS;
-        if ((passes & 1) && tmax > passes) ++passes;
-    }
+    int64_t passes, base, rem;
+    fdtd_plan(tmax, march, &passes, &base, &rem);
     g_fd_last = march ? 2 : 1;
-    const int64_t base = tmax / passes, rem = tmax % passes;
     // TMAX short dependent launches: capture once per (extents, pointers), replay as one graph
     npb::GraphKey key;
     memset(&key, 0, sizeof(key));

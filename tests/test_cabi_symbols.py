@@ -64,3 +64,31 @@ def test_argument_validation_mirrors_numpy_errors():
         nb.vadv(*(np.zeros((2, 2, 1)),) * 2, np.zeros((3, 2, 1)), *(np.zeros((2, 2, 1)),) * 2, 0.15)
     with pytest.raises(TypeError):
         nb.heat_3d(2, np.zeros((4, 4, 4), dtype=np.float32), np.zeros((4, 4, 4), dtype=np.float32))
+
+
+def test_fdtd2d_pass_plan_host_logic():
+    """npb_fdtd2d_pass_plan is pure host logic (no device call): the marching time loop must cover TMAX exactly,
+    with at most five steps per pass, evenly spread, and an even number of passes whenever TMAX >= 2 (the result then
+    ends in the caller's arrays without a copy-back); the per-step loop is TMAX passes of one step."""
+    import ctypes
+
+    import numpy as np
+
+    from npbench_b200 import _lib
+
+    L = _lib.lib()
+    buf = np.zeros(4096, dtype=np.int32)
+    ptr = ctypes.c_void_p(buf.ctypes.data)
+    assert L.fdtd2d_pass_plan(0, 1, ptr, buf.size) == 0
+    for tmax in list(range(1, 70)) + [150, 499, 500, 1000]:
+        n = L.fdtd2d_pass_plan(tmax, 1, ptr, buf.size)
+        plan = buf[:n].tolist()
+        assert sum(plan) == tmax and min(plan) >= 1 and max(plan) <= 5
+        assert max(plan) - min(plan) <= 1
+        assert n == 1 if tmax == 1 else n % 2 == 0
+        assert n <= (tmax + 4) // 5 + 1
+        m = L.fdtd2d_pass_plan(tmax, 0, ptr, buf.size)
+        assert m == tmax and buf[:m].tolist() == [1] * tmax
+    # cap smaller than the plan: count is still returned, only `cap` entries are written
+    buf[:] = -1
+    assert L.fdtd2d_pass_plan(50, 1, ptr, 3) == 10 and buf[:4].tolist() == [5, 5, 5, -1]
