@@ -5,15 +5,21 @@
 // consumes row r-s of state s and completes row r-s-1 of state s+1 from the two rows
 // of state s it keeps in registers, handing the result to sweep s+1 in registers.
 // The lateral neighbours of a lane's edge columns come from the neighbouring lanes
-// by shuffle.  No shared memory, no barriers (jacobi_2d_numpy.py:6-10: two sweeps
+// by shuffle.  No barriers, no shared tiles (jacobi_2d_numpy.py:6-10: two sweeps
 // per t, 0.2 * (c + left + right + down + up) in that order).
 //
 // NS is odd, so a pass goes src -> dst and state q's constant border equals dst's
-// border for odd q and src's for even q (the blocked kernel's parity argument):
-// border cells are re-read from the right array at every sweep (L1 hits after the
-// first; the border columns are prefetched a few rows ahead) and never written.
+// border for odd q and src's for even q (the blocked kernel's parity argument).
+// Border cells are never written.  Border rows are re-read from the right array
+// when a sweep completes row 0 or N-1 (a handful of row steps per chunk); the lane
+// that owns column 0 or N-1 keeps the src / dst values of the last 16 rows in a
+// private shared ring, loaded two rows ahead.  Row steps that can touch neither run
+// a check-free instantiation, two rows at a time and skewed by one sweep, so that
+// eight independent FP64 chains interleave per lane.
 // NS garbage columns per side, rounded up to whole lanes: 112 of 128 columns stored
-// for NS = 5 or 7.  Rows are cut into chunks with an NS-row ramp above and below.
+// for NS = 5 or 7, 120 for NS = 3.  Rows are cut into chunks with an NS-row ramp
+// above and below; a launch may be restricted to a row range (the sharded driver's
+// boundary / interior split).
 //
 // Traffic per cell and pass at NS = 7: 8 B * 128/112 read + 8 B written = 17.1 B,
 // i.e. 2.4 B per cell update against 16 B.
