@@ -151,7 +151,7 @@ extern "C" int npb_adi_f64(int64_t tsteps, int64_t n, double *u) {
         npb::count_launch(2);
     }
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

@@ -144,7 +144,7 @@ extern "C" int npb_cavity_flow_f64(int64_t nx, int64_t ny, int64_t nt, int64_t n
             rc = npb::fail("npb_cavity_flow_f64", "copy failed");
     }
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

@@ -207,7 +207,7 @@ extern "C" int npb_channel_flow_f64(int64_t nit, int64_t nx, int64_t ny, double 
             int rc = enqueue_sum(ubuf[uc_in ^ 1]);
             if (cudaGetLastError() != cudaSuccess) rc = 1;
             if (capturing) {
-                const int rc2 = npb::graph_end_and_launch(key);
+                const int rc2 = npb::graph_end_and_launch(key, rc);
                 if (!rc) rc = rc2;
             }
             if (rc) return npb::fail("npb_channel_flow_f64", "kernel launch failed");

@@ -44,8 +44,9 @@ struct GraphKey {
 bool graph_replay(const GraphKey &key);
 // begin capturing the current stream; false if capture is not possible (then launch directly)
 bool graph_begin();
-// end capture, instantiate, cache under `key` and launch once; returns 0 or a CUDA error code
-int graph_end_and_launch(const GraphKey &key);
+// end capture; rc == 0: instantiate, cache under `key` and launch once (returns 0 or a CUDA error code);
+// rc != 0 (the caller's launch loop failed): discard the partial graph and return rc
+int graph_end_and_launch(const GraphKey &key, int rc);
 
 }  // namespace npb
 

@@ -176,7 +176,7 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
                 rc = npb::fail_cuda("fdtd2d copy-back", cudaGetLastError());
     }
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

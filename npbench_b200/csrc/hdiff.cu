@@ -278,6 +278,9 @@ int g_hdiff_last = 0;        // 1 marching, 2 ring
 // Returns 1 if the ring kernel was launched, 0 if not applicable.
 int try_ring(int64_t I, int64_t J, int64_t K, const double *in, double *out, const double *coeff, bool force) {
     if ((K & 1) || K > ring::CONSUMERS || K < 2) return 0;           // 16-byte aligned rows; one row tile per CTA
+    // cp.async.bulk needs 16-byte aligned global addresses (a misaligned one is a sticky fault); K even
+    // only guarantees the row stride, so a view offset by an odd number of doubles takes the marching kernel
+    if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)coeff) & 15) return 0;
     int TJ = 2 * (int)(ring::CONSUMERS / K);                       // column pairs x K threads <= CONSUMERS
     if (TJ > J) TJ = (int)((J + 1) & ~1LL);
     if (TJ < 2) return 0;

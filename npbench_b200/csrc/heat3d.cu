@@ -849,7 +849,7 @@ extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2
         if (!rc) rc = launch_sweep(n0, n1, n2, B, A, 1, n0 - 1);
     }
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

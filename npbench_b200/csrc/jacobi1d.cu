@@ -128,7 +128,7 @@ extern "C" int npb_jacobi1d_f64(int64_t tsteps, int64_t n, double *A, double *B)
     }
     if (!rc) rc = launch_pass(1, n, src, dst);   // src == B (state S-1), dst == A
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

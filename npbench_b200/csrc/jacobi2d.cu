@@ -480,7 +480,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
     // now src == B (state S-1), dst == A
     if (!rc) rc = launch_block(tile, 1, ni, nj, src, dst, 0, -1);
     if (capturing) {
-        const int rc2 = npb::graph_end_and_launch(key);
+        const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;
     }
     return rc;

@@ -89,9 +89,18 @@ bool graph_begin() {
     return true;
 }
 
-int graph_end_and_launch(const GraphKey &key) {
+int graph_end_and_launch(const GraphKey &key, int rc) {
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(st().stream, &graph);
+    if (rc != 0) {
+        // the caller's launch loop stopped early (a host-side reject issues no CUDA error, so the capture
+        // ends cleanly with a PARTIAL graph): drop it -- neither cache nor launch -- and keep the caller's
+        // error message; the next identical call captures again and fails the same way
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        st().launches = g_capture_launch_base;
+        return rc;
+    }
     if (e != cudaSuccess || !graph) return fail_cuda("cudaStreamEndCapture", e == cudaSuccess ? cudaErrorUnknown : e);
     GraphEntry *slot = &g_graphs[0];
     for (auto &g : g_graphs) {

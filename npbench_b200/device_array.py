@@ -31,10 +31,21 @@ class DeviceArray:
             self._owner = _owner if _owner is not None else True
 
     # -- construction / extraction -------------------------------------------
+    @staticmethod
+    def _host_f64(a) -> np.ndarray:
+        """C-contiguous float64 view/copy of `a`.  Other dtypes are REJECTED, not upcast: the harness
+        validates against NumPy run on the same arrays, so a silent cast would compare different
+        precisions (kernels._kind rejects the same input on the host-buffer path)."""
+        a = np.asarray(a)
+        if a.dtype != np.float64:
+            raise TypeError("the B200 stencil backend computes in float64 only (got %s); NPBench's default "
+                            "datatype for these kernels is float64" % a.dtype)
+        return np.ascontiguousarray(a)
+
     @classmethod
     def from_host(cls, a) -> "DeviceArray":
         """Framework.copy_func: np.ndarray -> device (async on the library stream)."""
-        a = np.ascontiguousarray(a, dtype=np.float64)
+        a = cls._host_f64(a)
         d = cls(a.shape)
         if d.nbytes:
             _lib.lib().h2d(d.ptr, a.ctypes.data, d.nbytes)
@@ -50,7 +61,7 @@ class DeviceArray:
         return out
 
     def copy_from_host(self, a) -> None:
-        a = np.ascontiguousarray(a, dtype=np.float64)
+        a = self._host_f64(a)
         assert a.shape == self.shape
         if self.nbytes:
             _lib.lib().h2d(self.ptr, a.ctypes.data, self.nbytes)

@@ -26,6 +26,8 @@ import torch
 import torch.distributed as dist
 
 JACOBI_MAX_BLOCK = 7   # == NPB_JACOBI2D_MAX_BLOCK
+FDTD_GHOST = 4         # ghost rows of the fdtd_2d slabs = steps between halo exchanges
+HEAT_GHOST = 4         # ghost planes of the heat_3d slabs = sweeps between halo exchanges
 
 
 # --------------------------------------------------------------------------- partition

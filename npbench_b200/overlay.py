@@ -11,15 +11,88 @@ text plus the single registration line frameworks.md:39-42 asks for.
 `run_cli` then executes the reference's own run_benchmark.py / run_framework.py byte for
 byte via runpy (a symlinked script would put the reference dir back on sys.path[0]).
 """
+import hashlib
 import importlib.util
+import json
 import os
 import runpy
 import shutil
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
 PLUGIN = os.path.join(_HERE, "plugin")
 REGISTRATION_LINE = "from .b200_framework import *\n"
+STAGED = os.path.join(_REPO, "baseline", "_ref")          # git-ignored; travels to the GPU box with the snapshot
+_STAGE_ITEMS = ("npbench", "bench_info", "framework_info", "run_benchmark.py", "run_framework.py", "LICENSE")
+MANIFEST = "B200_STAGE_MANIFEST.json"
+
+
+def is_checkout(path: str) -> bool:
+    return bool(path) and all(os.path.isdir(os.path.join(path, d)) for d in ("npbench", "bench_info", "framework_info"))
+
+
+def find_reference(explicit: str = None) -> str:
+    """An unmodified NPBench checkout: --reference / $NPBENCH_REF, /root/reference (build container),
+    or the byte-for-byte staged copy under baseline/_ref (GPU box).  Raises when none is present."""
+    tried = []
+    for cand in (explicit, os.environ.get("NPBENCH_REF"), "/root/reference", STAGED):
+        if cand:
+            tried.append(cand)
+            if is_checkout(cand):
+                return os.path.abspath(cand)
+    raise FileNotFoundError("no NPBench checkout found (tried %s); stage one with "
+                            "`python -m npbench_b200.overlay --stage <checkout>`" % ", ".join(tried))
+
+
+def _sha(path: str) -> str:
+    with open(path, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def stage_reference(src: str, dest: str = STAGED) -> str:
+    """Copy the harness-relevant part of an NPBench checkout, byte for byte, to baseline/_ref so that
+    the UNMODIFIED harness can run on a box where /root/reference is not mounted.  Writes a manifest
+    (relative path -> sha256 of the source file) that verify_staged() re-checks."""
+    src, dest = os.path.abspath(src), os.path.abspath(dest)
+    if not is_checkout(src):
+        raise FileNotFoundError("%s is not an NPBench checkout" % src)
+    if os.path.isdir(dest):
+        shutil.rmtree(dest)
+    os.makedirs(dest)
+    manifest = {}
+    for item in _STAGE_ITEMS:
+        s = os.path.join(src, item)
+        if os.path.isdir(s):
+            for dirpath, dirnames, filenames in os.walk(s):
+                dirnames[:] = sorted(d for d in dirnames if d != "__pycache__")
+                for f in sorted(filenames):
+                    if f.endswith((".pyc", ".db")):
+                        continue
+                    rel = os.path.relpath(os.path.join(dirpath, f), src)
+                    os.makedirs(os.path.dirname(os.path.join(dest, rel)), exist_ok=True)
+                    shutil.copyfile(os.path.join(src, rel), os.path.join(dest, rel))
+                    manifest[rel] = _sha(os.path.join(src, rel))
+        elif os.path.isfile(s):
+            shutil.copyfile(s, os.path.join(dest, item))
+            manifest[item] = _sha(s)
+    with open(os.path.join(dest, MANIFEST), "w") as f:
+        json.dump({"source": src, "files": manifest}, f, indent=0, sort_keys=True)
+    return dest
+
+
+def verify_staged(dest: str = STAGED):
+    """[(relative path, problem)] for every staged file that no longer matches its manifest hash."""
+    with open(os.path.join(dest, MANIFEST)) as f:
+        files = json.load(f)["files"]
+    bad = []
+    for rel, h in files.items():
+        p = os.path.join(dest, rel)
+        if not os.path.isfile(p):
+            bad.append((rel, "missing"))
+        elif _sha(p) != h:
+            bad.append((rel, "modified"))
+    return bad
 
 
 def _mirror(src_root: str, dst_root: str) -> None:
@@ -80,6 +153,7 @@ def prepare_sys_path(overlay: str) -> None:
 
 def run_cli(reference: str, overlay: str, script: str, argv) -> None:
     """Execute <reference>/<script> (e.g. run_benchmark.py) unmodified with `argv`."""
+    reference = find_reference(reference)
     build_overlay(reference, overlay)
     prepare_sys_path(overlay)
     old = sys.argv
@@ -88,3 +162,10 @@ def run_cli(reference: str, overlay: str, script: str, argv) -> None:
         runpy.run_path(os.path.join(reference, script), run_name="__main__")
     finally:
         sys.argv = old
+
+
+if __name__ == "__main__":      # python -m npbench_b200.overlay --stage <checkout>
+    if len(sys.argv) == 3 and sys.argv[1] == "--stage":
+        print(stage_reference(sys.argv[2]))
+    else:
+        print(find_reference())

@@ -10,6 +10,7 @@ import argparse
 import os
 import sys
 import tempfile
+import zlib
 
 from . import overlay as _ov
 
@@ -21,12 +22,16 @@ def main(argv=None):
         i = argv.index("--")
         argv, rest = argv[:i], argv[i + 1:]
     ap = argparse.ArgumentParser(prog="npbench_b200.run")
-    ap.add_argument("--reference", default=os.environ.get("NPBENCH_REF", "/root/reference"))
+    ap.add_argument("--reference", default=None,
+                    help="NPBench checkout (default: $NPBENCH_REF, /root/reference, baseline/_ref)")
     ap.add_argument("--overlay", default=None)
     ap.add_argument("--script", default="run_benchmark.py")
     a = ap.parse_args(argv)
-    ov = a.overlay or os.path.join(tempfile.gettempdir(), "npbench_b200_overlay")
-    _ov.run_cli(a.reference, ov, a.script, rest)
+    ref = _ov.find_reference(a.reference)
+    # one overlay per checkout: symlinks into a different checkout must not be reused
+    tag = "%08x" % zlib.crc32(ref.encode())
+    ov = a.overlay or os.path.join(tempfile.gettempdir(), "npbench_b200_overlay_" + tag)
+    _ov.run_cli(ref, ov, a.script, rest)
 
 
 if __name__ == "__main__":

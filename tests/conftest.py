@@ -28,6 +28,13 @@ def pins():
 
 
 @pytest.fixture(scope="session")
+def pins_large():
+    """Reference pins at presets L and paper (tests/golden/make_golden_large.py)."""
+    with open(os.path.join(GOLDEN, "pins_large.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def cases():
     """tests/golden/cases.npz regrouped as {bench: [ {field: array}, ... ]}."""
     z = np.load(os.path.join(GOLDEN, "cases.npz"))

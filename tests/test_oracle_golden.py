@@ -127,3 +127,48 @@ def test_slab_initialisers_match_full():
     ex, ey, hz, f = oracle.init_fdtd_2d(5, 20, 30)
     x, y, z, _ = oracle.init_fdtd_2d(5, 20, 30, row0=11, nrows=5)
     assert_bit_equal(x, ex[11:16]); assert_bit_equal(y, ey[11:16]); assert_bit_equal(z, hz[11:16])
+
+
+def test_large_presets_against_reference_pins(pins_large):
+    """Presets L and `paper` (tests/golden/make_golden_large.py: sha256 of the unmodified reference's outputs;
+    jacobi_2d paper is a 160 s NumPy run there, 5 s here).  heat_3d also on seeded random inputs, because its
+    NPBench input is a fixed point of the stencil."""
+    oracle.set_threads(oracle.max_threads())
+    try:
+        for preset in ("L", "paper"):
+            p = oracle.PRESETS["jacobi_2d"][preset]; pin = pins_large["jacobi_2d/" + preset]
+            A, B = oracle.init_jacobi_2d(p["N"])
+            oracle.jacobi_2d(p["TSTEPS"], A, B)
+            _check(pin, "A", A, "out"); _check(pin, "B", B, "out")
+
+            p = oracle.PRESETS["heat_3d"][preset]; pin = pins_large["heat_3d/" + preset]
+            A, B = oracle.init_heat_3d(p["N"])
+            oracle.heat_3d(p["TSTEPS"], A, B)
+            _check(pin, "A", A, "out"); _check(pin, "B", B, "out")
+            pin = pins_large["heat_3d_random/" + preset]
+            rng = np.random.default_rng(pins_large["heat_3d_random_seed"])
+            A = rng.random((p["N"],) * 3); B = rng.random((p["N"],) * 3)
+            _check(pin, "A", A, "in"); _check(pin, "B", B, "in")
+            oracle.heat_3d(p["TSTEPS"], A, B)
+            _check(pin, "A", A, "out"); _check(pin, "B", B, "out")
+
+            p = oracle.PRESETS["fdtd_2d"][preset]; pin = pins_large["fdtd_2d/" + preset]
+            ex, ey, hz, fict = oracle.init_fdtd_2d(p["TMAX"], p["NX"], p["NY"])
+            oracle.fdtd_2d(p["TMAX"], ex, ey, hz, fict)
+            for n, a in (("ex", ex), ("ey", ey), ("hz", hz)):
+                _check(pin, n, a, "out")
+
+            p = oracle.PRESETS["hdiff"][preset]; pin = pins_large["hdiff/" + preset]
+            inf, outf, coeff = oracle.init_hdiff(p["I"], p["J"], p["K"])
+            _check(pin, "in_field", inf, "in"); _check(pin, "coeff", coeff, "in")
+            oracle.hdiff(inf, outf, coeff)
+            _check(pin, "out_field", outf, "out")
+
+            p = oracle.PRESETS["vadv"][preset]; pin = pins_large["vadv/" + preset]
+            dtr, us, u, w, up, ut = oracle.init_vadv(p["I"], p["J"], p["K"])
+            assert dtr == pin["dtr_stage"]
+            _check(pin, "utens_stage", us, "in"); _check(pin, "wcon", w, "in")
+            oracle.vadv(us, u, w, up, ut, dtr)
+            _check(pin, "utens_stage", us, "out")
+    finally:
+        oracle.set_threads(1)

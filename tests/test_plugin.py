@@ -17,8 +17,13 @@ import pytest
 import oracle
 from conftest import ROOT, assert_bit_equal
 
-REF = os.environ.get("NPBENCH_REF", "/root/reference")
-needs_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "npbench")), reason="no NPBench checkout")
+from npbench_b200 import overlay as _overlay
+
+try:
+    REF = _overlay.find_reference()          # $NPBENCH_REF, /root/reference, or the staged baseline/_ref
+except FileNotFoundError:
+    REF = ""
+needs_ref = pytest.mark.skipif(not REF, reason="no NPBench checkout")
 
 
 def test_descriptor_has_the_keys_the_harness_reads():

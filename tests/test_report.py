@@ -62,3 +62,11 @@ def test_cli(tmp_path, capsys):
     report.main(["--db", db, "--bench-json", os.path.join(ROOT, "profiles", "r01_bench_n1.json")])
     out = capsys.readouterr().out
     assert "imported" in out and "heat3d" in out and "b200" in out
+
+
+def test_channel_flow_step_counts_are_the_pinned_reference_values(pins_large):
+    """report.py's unit count of channel_flow = steps until the reference's convergence loop stops
+    (tests/golden/make_golden_large.py pins it from the unmodified reference at every preset)."""
+    from npbench_b200 import report
+    for preset, p in report.BENCH["channel_flow"]["presets"].items():
+        assert p["steps"] == pins_large["channel_flow/" + preset]["stepcount"], preset
