@@ -91,15 +91,18 @@ int npb_jacobi2d_tile_rows(void);        /* rows per tile of the blocked kernel 
 
 /* kernel(TSTEPS, A, B): polybench/heat_3d/heat_3d_numpy.py:4-20.  (n0,n1,n2). */
 int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A, double *B);
-/* 0 = dispatch by size (on-chip resident persistent kernel with in-L2 halo inboxes when the grid
- * fits in shared memory; grids of >= 40M cells with n1, n2 >= 128: three sweeps per pass over HBM,
- * heat3d_march_kernel; else one streaming launch per sweep, replayed as a CUDA graph);
- * 1 = always streaming; 2 = same as 0 without the streaming fallback order change;
- * 3 = temporally blocked shared-memory passes (3 sweeps per launch); 4 = resident kernel with two
- * sweeps per halo exchange.  3 and 4 are measured slower and kept for comparison.
- * 5 = three-sweep marching passes at any shape with n0 >= 8.  +8: no graph. */
+/* mode & 7: 0 = dispatch by size (grids that fit on chip -- NPBench S / M / L -- run in ONE cooperative launch:
+ * heat3d_regtile_kernel, cell state in registers, faces through shared memory, halos through in-L2 inboxes;
+ * if its limits do not fit, heat3d_resident_kernel (state in shared memory); grids of >= 40M cells with
+ * n1, n2 >= 128: three sweeps per pass over HBM, heat3d_march_kernel; else one streaming launch per sweep,
+ * replayed as a CUDA graph); 1 = always streaming; 2 = the shared-memory resident kernel when eligible;
+ * 5 = three-sweep marching passes at any shape with n0 >= 8; 6 = the register-tile kernel or an error.
+ * +8: no graph.  +256 / +512 / +1024: timing experiments of the register-tile kernel (no fences / no polls /
+ * no sends -- results are wrong by construction).  A failed cooperative launch is an error, never a silent
+ * fallback to a slower path. */
 int npb_heat3d_set_mode(int mode);
-int npb_heat3d_last_path(void);          /* last call: 1/4 resident, 2 streaming, 3 blocked, 5 marching */
+int npb_heat3d_last_path(void);          /* last call: 1 shared-memory resident, 2 streaming, 5 marching, 6 register-tile resident */
+int npb_heat3d_set_trace(void *dev_buf); /* profiling aid: 10 int64 phase cycle counters of the register-tile kernel's centre CTA, NULL = off */
 /* one sweep src -> dst over planes [i_lo, i_hi) (clamped to the interior) */
 int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
                          int64_t i_lo, int64_t i_hi);

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "npb_fdtd2d_pass_plan": (_int, [_i64, _int, _vp, _int]),
     "npb_heat3d_set_mode": (_int, [_int]),
     "npb_heat3d_last_path": (_int, []),
+    "npb_heat3d_set_trace": (_int, [_vp]),
     "npb_heat3d_sweep_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _i64, _i64]),
     "npb_fdtd2d_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "npb_fdtd2d_step_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64]),

@@ -1,0 +1,41 @@
+"""Phase cycle counters of heat3d_regtile_kernel's centre CTA (development aid, GPU only).
+
+    python tools/heat_trace.py [N [TSTEPS]]
+Prints, for thread 0 (a corner block: two halo sides) and the middle thread, the average cycles per sweep spent in
+[faces + halo-independent arithmetic | waiting for halo values | halo-dependent arithmetic + sends | re-arm + publish | fence + barrier].
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import npbench_b200 as nb
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 70
+    ts = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+    nb.init(0)
+    L = nb.lib()
+    A = nb.DeviceArray((n, n, n)); B = nb.DeviceArray((n, n, n))
+    L.init_heat3d_f64(n, 0, n, A.ptr, B.ptr)
+    tr = nb.DeviceArray((10,))
+    for mode in [int(m) for m in os.environ.get("MODES", "6,262,518,1798").split(",")]:
+        L.heat3d_set_mode(mode)
+        L.memset(tr.ptr, 0, 80)
+        L.heat3d_set_trace(tr.ptr)
+        for _ in range(3):
+            nb.heat_3d(ts, A, B)
+        L.sync()
+        L.heat3d_set_trace(None)
+        L.heat3d_set_mode(0)
+        raw = np.frombuffer(tr.to_host().tobytes(), dtype=np.int64).astype(np.float64) / (2 * (ts - 1))
+        for who, v in (("thread 0 (corner block)", raw[:5]), ("middle thread", raw[5:])):
+            print("N=%d mode=%4d %-24s: early %6.0f | wait %6.0f | late+send %6.0f | arm+publish %6.0f | fence+barrier %6.0f | sum %6.0f cycles/sweep"
+                  % (n, mode, who, v[0], v[1], v[2], v[3], v[4], v.sum()))
+
+
+if __name__ == "__main__":
+    main()
