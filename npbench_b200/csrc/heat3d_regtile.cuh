@@ -41,8 +41,8 @@
 
 namespace regtile {
 
-constexpr int SLOTS = 12;          // inbox ring depth (sweeps)
-constexpr int FENCE_EVERY = 4;     // gpu-scope fence cadence (sweeps); needs 2 * cadence <= SLOTS (see inbox.cuh)
+constexpr int SLOTS = 16;          // inbox ring depth (sweeps)
+constexpr int FENCE_EVERY = 8;     // gpu-scope fence cadence (sweeps); needs 2 * cadence <= SLOTS (see inbox.cuh)
 
 struct Params {
     int n0, n1, n2;
