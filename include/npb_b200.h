@@ -103,6 +103,12 @@ int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A
 int npb_heat3d_set_mode(int mode);
 int npb_heat3d_last_path(void);          /* last call: 1 shared-memory resident, 2 streaming, 5 marching, 6 register-tile resident */
 int npb_heat3d_set_trace(void *dev_buf); /* profiling aid: 10 int64 phase cycle counters of the register-tile kernel's centre CTA, NULL = off */
+/* THREE sweeps src -> dst in one pass over memory (heat3d_march_kernel; reference loop body heat_3d_numpy.py:7-19),
+ * output planes [i_lo, i_hi) (clamped to the interior).  State 1 takes its constant j / k borders from dst, state 2
+ * from src, exactly as three one-sweep launches src -> dst -> src -> dst would.  On a slab, planes closer than 3 to
+ * an edge that is not a grid edge come out as garbage: the caller keeps >= 3 ghost planes. */
+int npb_heat3d_march_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
+                         int64_t i_lo, int64_t i_hi);
 /* one sweep src -> dst over planes [i_lo, i_hi) (clamped to the interior) */
 int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
                          int64_t i_lo, int64_t i_hi);
@@ -128,6 +134,15 @@ int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrows, int64_t 
                         const double *ex, const double *ey, const double *hz,
                         double *ex_out, double *ey_out, double *hz_out, double fict_t,
                         int64_t row_lo, int64_t row_hi);
+
+/* ns (2..5) fused time steps on a row slab in ONE pass over memory (fdtd2d_march_kernel; the reference loop body is
+ * fdtd_2d_numpy.py:6-11): src fields -> dst fields, output rows [row_lo, row_hi) (0, -1 for all).  `fict_dev` points
+ * at _fict_[t] of the first step IN DEVICE MEMORY (ns consecutive values are read).  Rows closer than ns to a slab
+ * edge that is not a grid edge come out as garbage: the caller keeps >= ns ghost rows (npbench_b200/distributed.py). */
+int npb_fdtd2d_march_f64(int ns, int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
+                         const double *ex, const double *ey, const double *hz,
+                         double *ex_out, double *ey_out, double *hz_out, const double *fict_dev,
+                         int64_t row_lo, int64_t row_hi);
 
 /* hdiff(in_field, out_field, coeff): weather_stencils/hdiff/hdiff_numpy.py:5-29.
  * in (I+4, J+4, K); out, coeff (I, J, K). */

@@ -51,6 +51,8 @@ PROTOTYPES = {
     "npb_heat3d_last_path": (_int, []),
     "npb_heat3d_set_trace": (_int, [_vp]),
     "npb_heat3d_sweep_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _i64, _i64]),
+    "npb_heat3d_march_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _i64, _i64]),
+    "npb_fdtd2d_march_f64": (_int, [_int, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64]),
     "npb_fdtd2d_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "npb_fdtd2d_step_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _i64, _i64]),
     "npb_hdiff_f64": (_int, [_i64, _i64, _i64, _vp, _vp, _vp]),

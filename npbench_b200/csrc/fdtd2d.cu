@@ -131,6 +131,19 @@ extern "C" int npb_fdtd2d_step_f64(int64_t nx_global, int64_t row0, int64_t nrow
     return launch_step(p);
 }
 
+// ns (2..5) steps src -> dst over the output rows [row_lo, row_hi) of a row slab (fdtd2d_march_kernel): the building
+// block of the sharded driver's passes.  `fict_dev` points at _fict_[t] of the pass's first step IN DEVICE MEMORY.
+// Rows within ns of a slab edge that is not a grid edge come out as garbage (ghost rows, >= ns deep by contract).
+extern "C" int npb_fdtd2d_march_f64(int ns, int64_t nx_global, int64_t row0, int64_t nrows, int64_t ny,
+                                    const double *ex, const double *ey, const double *hz, double *ex_out,
+                                    double *ey_out, double *hz_out, const double *fict_dev, int64_t row_lo,
+                                    int64_t row_hi) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nrows >= 2 && ny >= 1 && row0 >= 0 && row0 + nrows <= nx_global, "npb_fdtd2d_march_f64", "slab outside the grid");
+    NPB_ARG(ns >= 2 && ns <= FM_MAX_STEPS, "npb_fdtd2d_march_f64", "steps per pass out of range (2..5)");
+    return launch_march(ns, nrows, ny, ex, ey, hz, ex_out, ey_out, hz_out, fict_dev, g_fd_rc, row0, nx_global, row_lo, row_hi);
+}
+
 extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
                               double *hz, const double *fict) {
     NPB_REQUIRE_INIT();

@@ -32,7 +32,9 @@ __host__ __device__ constexpr int fm_out_cols(int ns) { return FM_STRIP - 2 * FM
 constexpr long long FM_AUTO_MIN_CELLS = 4000000;   // default dispatch: grids at least this large march
 
 struct FmParams {
-    long long nx, ny;
+    long long nx, ny;          // rows of the (local) array, columns
+    long long row0, nx_global; // local row 0 is global row row0 of an nx_global-row grid (row slabs: distributed.py)
+    long long row_lo, row_hi;  // output rows [row_lo, row_hi) of this launch
     long long nstrips;
     int rc;                    // output rows per chunk
     int pfd;                   // L2 prefetch distance in rows (0 = off)
@@ -90,8 +92,9 @@ fdtd2d_march_kernel(FmParams p) {
     const long long col0 = strip * fm_out_cols(NS) - FM_COLS * HL + FM_COLS * lane;
     const bool full = col0 >= 0 && col0 + FM_COLS <= ny;
     const bool storing = lane >= HL && lane < 32 - HL;
-    const long long r0 = (long long)blockIdx.y * p.rc;
-    const long long r1 = (r0 + p.rc < nx) ? r0 + p.rc : nx;          // output rows [r0, r1)
+    const long long r0 = p.row_lo + (long long)blockIdx.y * p.rc;
+    const long long r1 = (r0 + p.rc < p.row_hi) ? r0 + p.rc : p.row_hi;   // output rows [r0, r1)
+    const bool top_slab = (p.row0 == 0);
     const long long r_first = (r0 - NS > 0) ? r0 - NS : 0;
     const long long r_last = r1 - 1 + NS;                            // rows >= nx are virtual (flush the pipeline)
     const long long r_load_last = (r_last < nx - 1) ? r_last : nx - 1;
@@ -134,7 +137,9 @@ fdtd2d_march_kernel(FmParams p) {
             const long long q = r - s;                   // row of state s being consumed; completes row q-1 of state s+1
             const double hz_lane_left = fm_shfl_up(hz_o[FM_COLS - 1]);
             const double ex_lane_right = fm_shfl_down(exn[s][0]);
-            const bool top = (q == 0), upd_hz = (q - 1 < nx - 1);
+            // the first / last LOCAL row of an inner slab is a ghost row: whatever is computed there is garbage that the
+            // caller's ghost depth absorbs; only the grid's own first row takes _fict_ (the last local row always keeps hz)
+            const bool top = (q == 0) && top_slab, upd_hz = (q - 1 < nx - 1);
             double out_hz[FM_COLS], ex_new[FM_COLS], ey_new[FM_COLS];
 #pragma unroll
             for (int m = 0; m < FM_COLS; ++m) {
@@ -175,25 +180,32 @@ int launch_march_ns(const FmParams &p, dim3 grid, bool vec) {
     return 0;
 }
 
-// one pass: ns (2..FM_MAX_STEPS) steps src -> dst
+// one pass: ns (2..FM_MAX_STEPS) steps src -> dst over the output rows [row_lo, row_hi) of an nx-row array whose row 0
+// is global row `row0` of an nx_global-row grid (whole grid: row0 = 0, nx_global = nx, all rows)
 int launch_march(int ns, int64_t nx, int64_t ny, const double *ex, const double *ey, const double *hz, double *exo,
-                 double *eyo, double *hzo, const double *fict_t, int rc_override) {
+                 double *eyo, double *hzo, const double *fict_t, int rc_override, int64_t row0 = 0, int64_t nx_global = -1,
+                 int64_t row_lo = 0, int64_t row_hi = -1) {
+    if (nx_global < 0) nx_global = nx;
+    if (row_lo < 0) row_lo = 0;
+    if (row_hi < 0 || row_hi > nx) row_hi = nx;
+    if (row_lo >= row_hi) return 0;
+    const long long span = row_hi - row_lo;
     const long long out_cols = fm_out_cols(ns);
     const long long nstrips = (ny + out_cols - 1) / out_cols;
     const long long blocks_x = (nstrips + FM_WARPS - 1) / FM_WARPS;
     // enough row chunks for ~48 warps per SM over the whole launch; each chunk re-runs 2*ns rows
     long long chunks = (48LL * npb::st().sm_count + nstrips - 1) / nstrips;
-    long long rc = (nx + chunks - 1) / chunks;
+    long long rc = (span + chunks - 1) / chunks;
     if (rc < 64) rc = 64;
     if (rc_override > 0) rc = rc_override;
-    if (rc > nx) rc = nx;
-    chunks = (nx + rc - 1) / rc;
+    if (rc > span) rc = span;
+    chunks = (span + rc - 1) / rc;
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("fdtd2d", "grid too large");
     const uintptr_t bits = (uintptr_t)ex | (uintptr_t)ey | (uintptr_t)hz | (uintptr_t)exo | (uintptr_t)eyo | (uintptr_t)hzo;
     const bool vec = (ny % 2 == 0) && (bits % 16 == 0);
     // measured at 8192 x 16384: 2.94 ms without, 2.71 ms at distance 2..4, 2.86 ms at 8
     static const int pfd = getenv("NPB_FDTD_PFD") ? atoi(getenv("NPB_FDTD_PFD")) : 3;
-    FmParams p{nx, ny, nstrips, (int)rc, pfd, ex, ey, hz, exo, eyo, hzo, fict_t};
+    FmParams p{nx, ny, row0, nx_global, row_lo, row_hi, nstrips, (int)rc, pfd, ex, ey, hz, exo, eyo, hzo, fict_t};
     dim3 grid((unsigned)blocks_x, (unsigned)chunks);
     switch (ns) {
         case 2: return launch_march_ns<2>(p, grid, vec);

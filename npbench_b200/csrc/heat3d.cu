@@ -479,6 +479,16 @@ extern "C" int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const do
     return launch_sweep(n0, n1, n2, src, dst, i_lo, i_hi);
 }
 
+// three sweeps src -> dst over the output planes [i_lo, i_hi) (heat3d_march_kernel): the building block of the
+// sharded driver's passes, like npb_jacobi2d_block_f64.  State 1 takes its constant borders from dst, state 2 from src.
+extern "C" int npb_heat3d_march_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst,
+                                    int64_t i_lo, int64_t i_hi) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(n0 >= 0 && n1 >= 0 && n2 >= 0, "npb_heat3d_march_f64", "negative extent");
+    NPB_ARG(march_eligible(n0, n1, n2), "npb_heat3d_march_f64", "shape not eligible for the marching kernel (n0 >= 8, n1, n2 >= 3)");
+    return launch_march(n0, n1, n2, src, dst, i_lo, i_hi);
+}
+
 extern "C" int npb_heat3d_f64(int64_t tsteps, int64_t n0, int64_t n1, int64_t n2, double *A,
                               double *B) {
     NPB_REQUIRE_INIT();

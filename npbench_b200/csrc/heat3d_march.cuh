@@ -36,6 +36,7 @@ struct HmParams {
     int n0, n1, n2;
     int tiles_k;
     int chunk;            // output planes per CTA along i
+    int i_lo, i_hi;       // output planes [i_lo, i_hi) of this launch (1 <= i_lo, i_hi <= n0 - 1)
     const double *src;
     double *dst;
 };
@@ -57,7 +58,7 @@ __device__ __forceinline__ void hm_march(const HmParams &p, double *S, int tj, i
     const int n0 = p.n0, n1 = p.n1, n2 = p.n2;
     const int gk = tk * HM_TK - 2 + rk;                  // region (r, rk) <-> global (gj0 + q, gk)
     const int gj0 = tj * HM_TJ - 2 + rb * HM_CPT;
-    const int ia = 1 + blockIdx.y * p.chunk, ib = min(ia + p.chunk, n0 - 1);   // output planes [ia, ib)
+    const int ia = p.i_lo + blockIdx.y * p.chunk, ib = min(ia + p.chunk, p.i_hi);   // output planes [ia, ib)
     const int L = max(0, ia - 3), E = min(n0, ib + 3);                         // source planes [L, E)
     const long long ps = (long long)n1 * n2;
     const long long off0 = (long long)gj0 * n2 + gk;
@@ -198,8 +199,14 @@ heat3d_march_kernel(HmParams p) {
     else hm_march<false>(p, S, tj, tk);
 }
 
-// one pass = three sweeps src -> dst
-int launch_march(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst) {
+// one pass = three sweeps src -> dst over the output planes [i_lo, i_hi) (clamped to the interior).  On a slab of a
+// sharded grid planes 0 and n0 - 1 are ghost planes, not constant borders: what the kernel makes of them is garbage
+// that creeps one plane per sweep, so the caller keeps >= 3 ghost planes per interior side (distributed.py).
+int launch_march(int64_t n0, int64_t n1, int64_t n2, const double *src, double *dst, int64_t i_lo = 1, int64_t i_hi = -1) {
+    if (i_lo < 1) i_lo = 1;
+    if (i_hi < 0 || i_hi > n0 - 1) i_hi = n0 - 1;
+    if (i_lo >= i_hi) return 0;
+    const long span = (long)(i_hi - i_lo);
     static bool configured = false;
     if (!configured) {
         NPB_CUDA(cudaFuncSetAttribute(heat3d_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HM_SMEM));
@@ -209,15 +216,15 @@ int launch_march(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     const long tiles = tiles_j * tiles_k, slots = 2L * npb::st().sm_count;
     // split i into chunks (each pays a 6-plane ramp) until the CTA count fills whole waves
     long best_nc = 1; double best_cost = 0.0;
-    for (long nc = 1; nc <= 32 && nc <= (n0 - 2); ++nc) {
-        const long planes = (n0 - 2 + nc - 1) / nc;
+    for (long nc = 1; nc <= 32 && nc <= span; ++nc) {
+        const long planes = (span + nc - 1) / nc;
         const long waves = (tiles * nc + slots - 1) / slots;
         const double cost = (double)waves * (double)(planes + 6);
         if (nc == 1 || cost < best_cost * 0.98) { best_nc = nc; best_cost = cost; }
     }
-    const long chunk = (n0 - 2 + best_nc - 1) / best_nc;
-    const long nchunks = (n0 - 2 + chunk - 1) / chunk;
-    HmParams p{(int)n0, (int)n1, (int)n2, (int)tiles_k, (int)chunk, src, dst};
+    const long chunk = (span + best_nc - 1) / best_nc;
+    const long nchunks = (span + chunk - 1) / chunk;
+    HmParams p{(int)n0, (int)n1, (int)n2, (int)tiles_k, (int)chunk, (int)i_lo, (int)i_hi, src, dst};
     dim3 grid((unsigned)tiles, (unsigned)nchunks);
     heat3d_march_kernel<<<grid, HM_THREADS, HM_SMEM, npb::st().stream>>>(p);
     NPB_CHECK_LAUNCH("heat3d_march_kernel");

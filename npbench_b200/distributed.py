@@ -26,8 +26,8 @@ import torch
 import torch.distributed as dist
 
 JACOBI_MAX_BLOCK = 7   # == NPB_JACOBI2D_MAX_BLOCK
-FDTD_GHOST = 4         # ghost rows of the fdtd_2d slabs = steps between halo exchanges
-HEAT_GHOST = 4         # ghost planes of the heat_3d slabs = sweeps between halo exchanges
+FDTD_GHOST = 5         # ghost rows of the fdtd_2d slabs = steps per marching pass (FM_MAX_STEPS) = steps between exchanges
+HEAT_GHOST = 3         # ghost planes of the heat_3d slabs = sweeps per marching pass = sweeps between exchanges
 
 
 # --------------------------------------------------------------------------- partition
@@ -136,6 +136,21 @@ class B200Engine:
         n0, n1, n2 = src.shape
         self._launch(self.lib.heat3d_sweep_f64, n0, n1, n2, src.data_ptr(), dst.data_ptr(), i_lo, i_hi)
 
+    def heat_march(self, src, dst, i_lo, i_hi):
+        """three sweeps src -> dst over the output planes [i_lo, i_hi) (heat3d_march_kernel)"""
+        n0, n1, n2 = src.shape
+        self._launch(self.lib.heat3d_march_f64, n0, n1, n2, src.data_ptr(), dst.data_ptr(), i_lo, i_hi)
+
+    def fict_on_device(self, fict):
+        return torch.tensor([float(x) for x in fict], dtype=torch.float64, device=self.torch_device)
+
+    def fdtd_march(self, ns, nx_global, row0, src, dst, fict_dev, t, r_lo, r_hi):
+        """ns (2..5) steps src -> dst over the output rows [r_lo, r_hi) (fdtd2d_march_kernel); fict_dev[t] = _fict_[t]"""
+        nrows, ny = src[0].shape
+        self._launch(self.lib.fdtd2d_march_f64, int(ns), nx_global, row0, nrows, ny, src[0].data_ptr(), src[1].data_ptr(),
+                     src[2].data_ptr(), dst[0].data_ptr(), dst[1].data_ptr(), dst[2].data_ptr(),
+                     fict_dev.data_ptr() + 8 * int(t), r_lo, r_hi)
+
     def fdtd_step(self, nx_global, row0, src, dst, fict_t, r_lo, r_hi):
         nrows, ny = src[0].shape
         self._launch(self.lib.fdtd2d_step_f64, nx_global, row0, nrows, ny, src[0].data_ptr(), src[1].data_ptr(),
@@ -213,12 +228,62 @@ def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch
         src, dst = dst, src
 
 
+def heat_plan(total_sweeps: int) -> List[int]:
+    """Passes of three sweeps (heat3d_march_kernel) and single sweeps: an even number of passes, the last one a
+    single sweep, so that state S ends in A and state S - 1 in B (run_march in csrc/heat3d_march.cuh: same plan)."""
+    if total_sweeps <= 0:
+        return []
+    m = total_sweeps - 1
+    n = (m + 2) // 3
+    if n % 2 == 0:
+        n += 1
+    triples = max(0, (m - n) // 2)
+    return [3] * triples + [1] * (n - triples) + [1]
+
+
+def _edge_ranges(slab: Slab, n: int, lo_edge: int, hi_edge: int) -> Tuple[int, int]:
+    """[b_lo, b_hi): the interior of the local rows [lo_edge, hi_edge); rows below b_lo feed the upward send, rows
+    from b_hi on the downward send (each H rows, next to the ghost rows)."""
+    H = slab.H
+    b_lo = min(hi_edge, slab.ht + H) if slab.ht else lo_edge
+    b_hi = max(b_lo, n - slab.hb - H) if slab.hb else hi_edge
+    return b_lo, b_hi
+
+
 def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.Tensor, group=None,
-                    exchanger=None) -> None:
-    """kernel(TSTEPS, A, B) of heat_3d_numpy.py:4-20 on an i-plane slab (ghost depth slab.H)."""
+                    exchanger=None, march=None) -> None:
+    """kernel(TSTEPS, A, B) of heat_3d_numpy.py:4-20 on an i-plane slab (ghost depth slab.H).  With a ghost depth of
+    at least 3 and an engine that has it, the sweeps run as marching passes (three sweeps per pass over memory,
+    heat3d_march_kernel) with one halo exchange per pass; otherwise one sweep per launch, one exchange per H sweeps."""
     ex = exchanger or HaloExchanger(slab, group)
     total = 2 * (TSTEPS - 1)
-    src, dst, done, H, n = A, B, 0, slab.H, slab.nloc
+    n, H = slab.nloc, slab.H
+    if march is None:
+        # every rank must take the same decision (the passes carry the exchanges): judge by the thinnest slab
+        thinnest = slab.n_global // slab.size + (H if slab.size > 1 else 0)
+        march = hasattr(engine, "heat_march") and (H >= 3 or slab.size == 1) and thinnest >= 8
+    src, dst = A, B
+    if march:
+        for k in heat_plan(total):
+            run = (lambda lo, hi: engine.heat_march(src, dst, lo, hi)) if k == 3 else \
+                  (lambda lo, hi: engine.heat_sweep(src, dst, lo, hi))
+            if slab.size == 1:
+                run(1, n - 1)
+            else:
+                # ghost planes are not computed: the exchange fills them
+                first, last = max(1, slab.ht), min(n - 1, n - slab.hb)
+                b_lo, b_hi = _edge_ranges(slab, n, first, last)
+                if b_lo > first:
+                    run(first, b_lo)
+                if b_hi < last:
+                    run(b_hi, last)
+                reqs = engine.start_exchange(ex, [dst], engine.boundary_done())
+                if b_hi > b_lo:
+                    run(b_lo, b_hi)                 # overlaps the halo transfer
+                engine.finish_exchange(reqs)
+            src, dst = dst, src
+        return
+    done = 0
     while done < total:
         k = min(H, total - done) if slab.size > 1 else total - done
         for s in range(k):
@@ -244,34 +309,63 @@ def heat_3d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch.T
 
 
 def fdtd_2d_sharded(engine, slab: Slab, TMAX: int, ex_: torch.Tensor, ey: torch.Tensor, hz: torch.Tensor,
-                    fict: Sequence[float], group=None, exchanger=None) -> None:
-    """kernel(TMAX, ex, ey, hz, _fict_) of fdtd_2d_numpy.py:4-11 on a row slab.  `fict` is a
-    host sequence (the reference indexes _fict_[t] on the host too)."""
+                    fict: Sequence[float], group=None, exchanger=None, march=None) -> None:
+    """kernel(TMAX, ex, ey, hz, _fict_) of fdtd_2d_numpy.py:4-11 on a row slab.  `fict` is a host sequence (the
+    reference indexes _fict_[t] on the host too).  With an engine that has it, the steps run as marching passes of up
+    to min(H, 5) steps per pass over memory (fdtd2d_march_kernel) with one halo exchange per pass; otherwise one
+    launch per step, one exchange per H steps."""
     exch = exchanger or HaloExchanger(slab, group)
     user = [ex_, ey, hz]
     work = [engine.empty(*f.shape) for f in user]
     src, dst, t, H, n = user, work, 0, slab.H, slab.nloc
-    while t < TMAX:
-        k = min(H, TMAX - t) if slab.size > 1 else TMAX - t
-        for s in range(k):
-            last = (s == k - 1) and slab.size > 1
-            f_t = float(fict[t + s])
-            if not last:
-                engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, n)
+    if march is None:
+        march = hasattr(engine, "fdtd_march") and slab.n_global // slab.size >= 2 and (H >= 2 or slab.size == 1)
+    if march:
+        fict_dev = engine.fict_on_device(fict)
+        cap = FDTD_GHOST if slab.size == 1 else min(H, FDTD_GHOST)
+        while t < TMAX:
+            k = min(cap, TMAX - t)
+            if k >= 2:
+                run = lambda lo, hi: engine.fdtd_march(k, slab.n_global, slab.row0, src, dst, fict_dev, t, lo, hi)
             else:
-                b_lo = min(n, slab.ht + H) if slab.ht else 0
-                b_hi = max(b_lo, n - slab.hb - H) if slab.hb else n
-                if b_lo > 0:
-                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, b_lo)
-                if b_hi < n:
-                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_hi, n)
+                run = lambda lo, hi: engine.fdtd_step(slab.n_global, slab.row0, src, dst, float(fict[t]), lo, hi)
+            if slab.size == 1:
+                run(0, n)
+            else:
+                first, last = slab.ht, n - slab.hb         # ghost rows are not computed: the exchange fills them
+                b_lo, b_hi = _edge_ranges(slab, n, first, last)
+                if b_lo > first:
+                    run(first, b_lo)
+                if b_hi < last:
+                    run(b_hi, last)
                 reqs = engine.start_exchange(exch, dst, engine.boundary_done())
                 if b_hi > b_lo:
-                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_lo, b_hi)
+                    run(b_lo, b_hi)                        # overlaps the halo transfer
                 engine.finish_exchange(reqs)
             src, dst = dst, src
-        t += k
-    if src is not user:          # an odd number of steps leaves the result in the workspace
+            t += k
+    else:
+        while t < TMAX:
+            k = min(H, TMAX - t) if slab.size > 1 else TMAX - t
+            for s in range(k):
+                last = (s == k - 1) and slab.size > 1
+                f_t = float(fict[t + s])
+                if not last:
+                    engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, n)
+                else:
+                    b_lo = min(n, slab.ht + H) if slab.ht else 0
+                    b_hi = max(b_lo, n - slab.hb - H) if slab.hb else n
+                    if b_lo > 0:
+                        engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, 0, b_lo)
+                    if b_hi < n:
+                        engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_hi, n)
+                    reqs = engine.start_exchange(exch, dst, engine.boundary_done())
+                    if b_hi > b_lo:
+                        engine.fdtd_step(slab.n_global, slab.row0, src, dst, f_t, b_lo, b_hi)
+                    engine.finish_exchange(reqs)
+                src, dst = dst, src
+            t += k
+    if src is not user:          # an odd number of passes leaves the result in the workspace
         for u, w in zip(user, src):
             engine.copy(u, w)
 

@@ -38,6 +38,41 @@ class CpuEngine:
         i_lo, i_hi = max(1, i_lo), min(src.shape[0] - 1, i_hi)
         dst.numpy()[i_lo:i_hi, 1:-1, 1:-1] = b[i_lo:i_hi, 1:-1, 1:-1]
 
+    def heat_march(self, src, dst, i_lo, i_hi):
+        """three sweeps src -> dst like heat3d_march_kernel: planes 0 / n-1 act as constant borders (state 1 takes them
+        from dst, state 2 from src); on a slab they are ghost planes, so everything within 3 planes of a slab edge that
+        is not a grid edge is garbage in the CUDA contract: poisoned here."""
+        a, b = src.numpy().copy(), dst.numpy().copy()
+        oracle.heat_3d_sweeps(3, a, b)
+        n = src.shape[0]
+        slab = self.slab
+        if slab.ht:
+            b[1:3] = np.nan
+        if slab.hb:
+            b[n - 3:n - 1] = np.nan
+        i_lo, i_hi = max(1, i_lo), min(n - 1, i_hi)
+        dst.numpy()[i_lo:i_hi, 1:-1, 1:-1] = b[i_lo:i_hi, 1:-1, 1:-1]
+
+    def fict_on_device(self, fict):
+        return np.asarray(fict, dtype=np.float64)
+
+    def fdtd_march(self, ns, nx_global, row0, src, dst, fict_dev, t, r_lo, r_hi):
+        """ns steps src -> dst like fdtd2d_march_kernel: rows within ns of a slab edge that is not a grid edge are garbage
+        in the CUDA contract (ghost rows): poisoned here."""
+        assert 2 <= ns <= 5
+        f = [x.numpy().copy() for x in src]
+        n = f[0].shape[0]
+        oracle.fdtd_2d(ns, f[0], f[1], f[2], np.ascontiguousarray(fict_dev[t:t + ns]))
+        if row0 > 0:
+            for x in f:
+                x[:ns] = np.nan
+        if row0 + n < nx_global:
+            for x in f:
+                x[n - ns:] = np.nan
+        r_hi = n if r_hi < 0 else r_hi
+        for d, x in zip(dst, f):
+            d.numpy()[r_lo:r_hi] = x[r_lo:r_hi]
+
     def fdtd_step(self, nx_global, row0, src, dst, fict_t, r_lo, r_hi):
         f = [x.numpy().copy() for x in src]
         n = f[0].shape[0]
@@ -83,24 +118,30 @@ def _worker(rank, size, port, case):
                 assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank)
                 assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank)
         elif case == "heat":
-            for ts, shape, H in ((2, (14, 6, 7), 3), (5, (17, 5, 6), 4), (8, (25, 6, 5), 3)):
+            for ts, shape, H in ((2, (14, 6, 7), 3), (5, (17, 5, 6), 4), (8, (25, 6, 5), 3), (7, (40, 5, 6), 3), (4, (36, 4, 5), 5)):
                 A, B = rng.random(shape), rng.random(shape)
-                slab = D.Slab(shape[0], size, rank, H)
-                lA, lB = _local(slab, A), _local(slab, B)
-                D.heat_3d_sharded(eng, slab, ts, lA, lB)
-                oracle.heat_3d(ts, A, B)
-                assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank)
-                assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank)
+                for march in (False, True):
+                    a, b = A.copy(), B.copy()
+                    slab = D.Slab(shape[0], size, rank, H)
+                    eng.slab = slab
+                    lA, lB = _local(slab, a), _local(slab, b)
+                    D.heat_3d_sharded(eng, slab, ts, lA, lB, march=march and shape[0] // size + H >= 8)
+                    oracle.heat_3d(ts, a, b)
+                    assert np.array_equal(slab.owned(lA).numpy(), a[slab.lo:slab.hi]), ("A", ts, rank, march)
+                    assert np.array_equal(slab.owned(lB).numpy(), b[slab.lo:slab.hi]), ("B", ts, rank, march)
         elif case == "fdtd":
-            for tm, (nx, ny), H in ((1, (12, 9), 2), (7, (23, 11), 3), (10, (30, 8), 4), (4, (19, 5), 5)):
+            for tm, (nx, ny), H in ((1, (12, 9), 2), (7, (23, 11), 3), (10, (30, 8), 4), (4, (19, 5), 5), (13, (41, 6), 5), (11, (33, 7), 7)):
                 ex, ey, hz = rng.random((nx, ny)), rng.random((nx, ny)), rng.random((nx, ny))
                 fict = rng.random(tm)
-                slab = D.Slab(nx, size, rank, H)
-                l = [_local(slab, f) for f in (ex, ey, hz)]
-                D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict)
-                oracle.fdtd_2d(tm, ex, ey, hz, fict)
-                for name, got, want in zip(("ex", "ey", "hz"), l, (ex, ey, hz)):
-                    assert np.array_equal(slab.owned(got).numpy(), want[slab.lo:slab.hi]), (name, tm, rank)
+                for march in (False, True):
+                    g = [f.copy() for f in (ex, ey, hz)]
+                    slab = D.Slab(nx, size, rank, H)
+                    eng.slab = slab
+                    l = [_local(slab, f) for f in g]
+                    D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict, march=march)
+                    oracle.fdtd_2d(tm, g[0], g[1], g[2], fict)
+                    for name, got, want in zip(("ex", "ey", "hz"), l, g):
+                        assert np.array_equal(slab.owned(got).numpy(), want[slab.lo:slab.hi]), (name, tm, rank, march)
         dist.barrier()
     finally:
         dist.destroy_process_group()

@@ -119,10 +119,12 @@ def test_jacobi_sharded_on_gpu(D, size):
         assert_bit_equal(b, wB[slab.lo:slab.hi], "B rank %d" % r)
 
 
+@pytest.mark.parametrize("march,H", [(False, 4), (True, 3), (True, 4)], ids=["per-sweep", "march-H3", "march-H4"])
 @pytest.mark.parametrize("size", [2, 3])
-def test_heat_sharded_on_gpu(D, size):
+def test_heat_sharded_on_gpu(D, size, march, H):
+    """march: three sweeps per pass (heat3d_march_kernel) over the slab's plane ranges, one exchange per pass"""
     rng = np.random.default_rng(2)
-    shape, ts, H = (61, 20, 33), 9, 4
+    shape, ts = (61, 20, 33), 9
     A, B = rng.random(shape), rng.random(shape)
     wA, wB = A.copy(), B.copy()
     oracle.heat_3d(ts, wA, wB)
@@ -132,7 +134,7 @@ def test_heat_sharded_on_gpu(D, size):
         eng = D.B200Engine(0)
         slab = D.Slab(shape[0], size, r, H)
         lA, lB = _dev(A, slab), _dev(B, slab)
-        D.heat_3d_sharded(eng, slab, ts, lA, lB, exchanger=LoopbackExchanger(slab, mb))
+        D.heat_3d_sharded(eng, slab, ts, lA, lB, exchanger=LoopbackExchanger(slab, mb), march=march)
         eng.synchronize()
         out[r] = (slab, slab.owned(lA).cpu().numpy(), slab.owned(lB).cpu().numpy())
 
@@ -142,10 +144,12 @@ def test_heat_sharded_on_gpu(D, size):
         assert_bit_equal(b, wB[slab.lo:slab.hi], "B rank %d" % r)
 
 
+@pytest.mark.parametrize("march,H", [(False, 4), (True, 4), (True, 5), (True, 2)], ids=["per-step", "march-H4", "march-H5", "march-H2"])
 @pytest.mark.parametrize("size,tm", [(2, 11), (3, 6)])
-def test_fdtd_sharded_on_gpu(D, size, tm):
+def test_fdtd_sharded_on_gpu(D, size, tm, march, H):
+    """march: min(H, 5) steps per pass (fdtd2d_march_kernel) over the slab's row ranges, one exchange per pass"""
     rng = np.random.default_rng(3)
-    nx, ny, H = 90, 301, 4
+    nx, ny = 90, 301
     f = [rng.random((nx, ny)) for _ in range(3)]
     fict = rng.random(tm)
     w = [x.copy() for x in f]
@@ -156,7 +160,7 @@ def test_fdtd_sharded_on_gpu(D, size, tm):
         eng = D.B200Engine(0)
         slab = D.Slab(nx, size, r, H)
         l = [_dev(x, slab) for x in f]
-        D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict, exchanger=LoopbackExchanger(slab, mb))
+        D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict, exchanger=LoopbackExchanger(slab, mb), march=march)
         eng.synchronize()
         out[r] = (slab, [slab.owned(x).cpu().numpy() for x in l])
 
@@ -164,6 +168,33 @@ def test_fdtd_sharded_on_gpu(D, size, tm):
     for r, (slab, got) in out.items():
         for name, g, want in zip(("ex", "ey", "hz"), got, w):
             assert_bit_equal(g, want[slab.lo:slab.hi], "%s rank %d" % (name, r))
+
+
+def test_march_entry_points_on_row_ranges(D):
+    """npb_fdtd2d_march_f64 / npb_heat3d_march_f64 on a whole grid, written range by range (boundary ranges first, like
+    the sharded driver): equal to ns steps / 3 sweeps of the oracle."""
+    eng = D.B200Engine(0)
+    rng = np.random.default_rng(17)
+    nx, ny, ns = 150, 260, 5
+    f = [rng.random((nx, ny)) for _ in range(3)]
+    fict = rng.random(ns)
+    src = [torch.from_numpy(x.copy()).cuda() for x in f]
+    dst = [torch.full_like(x, float("nan")) for x in src]
+    fd = eng.fict_on_device(fict)
+    for lo, hi in ((0, 7), (140, 150), (7, 64), (64, 140)):
+        eng.fdtd_march(ns, nx, 0, src, dst, fd, 0, lo, hi)
+    eng.synchronize()
+    oracle.fdtd_2d(ns, f[0], f[1], f[2], fict)
+    for name, g, w in zip(("ex", "ey", "hz"), dst, f):
+        assert_bit_equal(g.cpu().numpy(), w, name)
+    shape = (40, 30, 70)
+    A, B = rng.random(shape), rng.random(shape)
+    dA, dB = torch.from_numpy(A.copy()).cuda(), torch.from_numpy(B.copy()).cuda()
+    for lo, hi in ((1, 4), (33, 39), (4, 20), (20, 33)):
+        eng.heat_march(dA, dB, lo, hi)
+    eng.synchronize()
+    oracle.heat_3d_sweeps(3, A, B)
+    assert_bit_equal(dB.cpu().numpy(), B, "state 3 in dst"); assert_bit_equal(dA.cpu().numpy(), A, "src untouched")
 
 
 def test_halo_free_shards_on_gpu(D):

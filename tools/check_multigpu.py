@@ -54,25 +54,27 @@ def main():
     ok["jacobi_2d_march"] = bool(np.array_equal(slab.owned(lA).cpu().numpy(), A[slab.lo:slab.hi]) and
                                  np.array_equal(slab.owned(lB).cpu().numpy(), B[slab.lo:slab.hi]))
 
-    shape, ts, H = (24 * world + 5, 40, 50), 8, 4
-    A, B = rng.random(shape), rng.random(shape)
-    slab = D.Slab(shape[0], world, rank, H)
-    lA, lB = dev(A, slab), dev(B, slab)
-    D.heat_3d_sharded(eng, slab, ts, lA, lB)
-    eng.synchronize()
-    oracle.heat_3d(ts, A, B)
-    ok["heat_3d"] = bool(np.array_equal(slab.owned(lA).cpu().numpy(), A[slab.lo:slab.hi]) and
-                         np.array_equal(slab.owned(lB).cpu().numpy(), B[slab.lo:slab.hi]))
+    for name, march, H in (("heat_3d", False, 4), ("heat_3d_march", True, D.HEAT_GHOST)):
+        shape, ts = (24 * world + 5, 40, 50), 8
+        A, B = rng.random(shape), rng.random(shape)
+        slab = D.Slab(shape[0], world, rank, H)
+        lA, lB = dev(A, slab), dev(B, slab)
+        D.heat_3d_sharded(eng, slab, ts, lA, lB, march=march)
+        eng.synchronize()
+        oracle.heat_3d(ts, A, B)
+        ok[name] = bool(np.array_equal(slab.owned(lA).cpu().numpy(), A[slab.lo:slab.hi]) and
+                        np.array_equal(slab.owned(lB).cpu().numpy(), B[slab.lo:slab.hi]))
 
-    nx, ny, tm, H = 50 * world + 11, 700, 11, 4
-    f = [rng.random((nx, ny)) for _ in range(3)]
-    fict = rng.random(tm)
-    slab = D.Slab(nx, world, rank, H)
-    l = [dev(x, slab) for x in f]
-    D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict)
-    eng.synchronize()
-    oracle.fdtd_2d(tm, f[0], f[1], f[2], fict)
-    ok["fdtd_2d"] = all(bool(np.array_equal(slab.owned(g).cpu().numpy(), w[slab.lo:slab.hi])) for g, w in zip(l, f))
+    for name, march, H in (("fdtd_2d", False, 4), ("fdtd_2d_march", True, D.FDTD_GHOST)):
+        nx, ny, tm = 50 * world + 11, 700, 13
+        f = [rng.random((nx, ny)) for _ in range(3)]
+        fict = rng.random(tm)
+        slab = D.Slab(nx, world, rank, H)
+        l = [dev(x, slab) for x in f]
+        D.fdtd_2d_sharded(eng, slab, tm, l[0], l[1], l[2], fict, march=march)
+        eng.synchronize()
+        oracle.fdtd_2d(tm, f[0], f[1], f[2], fict)
+        ok[name] = all(bool(np.array_equal(slab.owned(g).cpu().numpy(), w[slab.lo:slab.hi])) for g, w in zip(l, f))
 
     flags = torch.tensor([int(v) for v in ok.values()], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
