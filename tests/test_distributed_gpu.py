@@ -193,8 +193,9 @@ def test_march_entry_points_on_row_ranges(D):
     for lo, hi in ((1, 4), (33, 39), (4, 20), (20, 33)):
         eng.heat_march(dA, dB, lo, hi)
     eng.synchronize()
-    oracle.heat_3d_sweeps(3, A, B)
-    assert_bit_equal(dB.cpu().numpy(), B, "state 3 in dst"); assert_bit_equal(dA.cpu().numpy(), A, "src untouched")
+    A0 = A.copy()
+    oracle.heat_3d_sweeps(3, A, B)          # the oracle ping-pongs: A ends as state 2, B as state 3
+    assert_bit_equal(dB.cpu().numpy(), B, "state 3 in dst"); assert_bit_equal(dA.cpu().numpy(), A0, "src untouched")
 
 
 def test_halo_free_shards_on_gpu(D):
