@@ -294,16 +294,23 @@ int try_ring(int64_t I, int64_t J, int64_t K, const double *in, double *out, con
     const int fit = (int)((npb::st().smem_optin - 1024) / slot_bytes);
     const int n_slots = fit >= 8 ? 8 : (fit >= 4 ? 4 : 0);
     if (n_slots == 0) return 0;
-    // rows per i-block: best load balance of the round-robin deal, then the longest block
+    // rows per i-block: the busiest CTA gets `rounds` units of the round-robin deal, each RB rows plus a 4-row ramp --
+    // minimise that; ties go to the fuller last round (more SMs busy), then to the longer block.  (Cutting the rows
+    // into equal contiguous j-tile-major ranges instead balances perfectly but was measured 12 % SLOWER at `paper`:
+    // CTAs on neighbouring j-tiles no longer walk the same rows at the same time, so the shared halo columns miss L2.)
     int RB = 8;
     {
-        double best = -1.0;
-        for (int rb = 8; rb <= 64; ++rb) {
-            const long long units = (long long)((I + rb - 1) / rb) * n_jtiles;
-            const long long rounds = (units + sms - 1) / sms;
-            const double eff = (double)units / (double)(rounds * sms) * ((double)rb / (rb + 4.0) * 0.25 + 0.75);
-            if (eff >= best) { best = eff; RB = rb; }
+        long best_rows = -1, best_units = 0;
+        const int rb_env = getenv("NPB_HDIFF_RB") ? atoi(getenv("NPB_HDIFF_RB")) : 0;
+        for (int rb = 8; rb <= 96; ++rb) {
+            const long units = (long)((I + rb - 1) / rb) * n_jtiles;
+            const long rounds = (units + sms - 1) / sms;
+            const long rows = rounds * (rb + 4);
+            if (best_rows < 0 || rows < best_rows || (rows == best_rows && units >= best_units)) {
+                best_rows = rows; best_units = units; RB = rb;
+            }
         }
+        if (rb_env > 0) RB = rb_env;
         if (RB > I) RB = (int)I;
     }
     const int n_iblocks = (int)((I + RB - 1) / RB);
