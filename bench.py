@@ -468,7 +468,8 @@ def record_kernel_name(L, bench):
                 4: "jacobi2d_regtile_kernel"}.get(int(L.jacobi2d_last_path()), "jacobi2d")
     if bench == "hdiff":
         return {1: "hdiff_march_kernel", 2: "hdiff_ring_kernel"}.get(int(L.hdiff_last_path()), "hdiff")
-    return {1: "vadv_pipeline_kernel", 2: "vadv_stream_kernel"}.get(int(L.vadv_last_path()), "vadv")
+    return {1: "vadv_pipeline_kernel", 2: "vadv_tma_kernel", 3: "vadv_stream_kernel (TMEM + TMA streaming Thomas solver)"}.get(
+        int(L.vadv_last_path()), "vadv")
 
 
 def host_case(nb, bench, p, rng):
@@ -801,7 +802,6 @@ def multi_gpu(args, world, rank, local_rank):
     ms = float(t.mean().item())
     units = weak_units(world)
     value = units / (ms * 1e-3) / 1e9
-    path = int(L.jacobi2d_last_path())
 
     # parity: one step from the initial state; every rank checks a band straddling its upper slab seam
     # (rank 0: the global top border), i.e. rows produced from exchanged halos
@@ -885,7 +885,7 @@ def multi_gpu(args, world, rank, local_rank):
                            "l2": "inputs (13.4 GB per GPU) far larger than L2; no flush needed",
                            "timing": "CUDA events per step, barrier + synchronize before each, max over ranks"},
                 "roofline": {"bound": "hbm", "kernel": "jacobi2d_march_kernel: 3/5/7 sweeps per pass in registers over the slab's row ranges "
-                                       "(csrc/jacobi2d_march.cuh, reached through npb_jacobi2d_block_f64); last path = %d" % path,
+                                       "(csrc/jacobi2d_march.cuh, reached through npb_jacobi2d_block_f64)",
                              "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": tr,
                              "frac_dram": round(tr / (pass_us * 1e-6) / 1e9 / peak, 4) if tr else None,

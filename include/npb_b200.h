@@ -47,7 +47,35 @@ int npb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
  * subsequent calls; NULL restores the library stream. */
 int npb_set_stream(void *cuda_stream);
 void *npb_get_stream(void);
-int npb_sync(void);                      /* the sync appended to exec_str (cupy_framework.py:56-58) */
+int npb_sync(void);                      /* the sync appended to exec_str (cupy_framework.py:56-58); waits for every
+                                          * device this process drives */
+
+/* ---- single-process multi-device (the `_mg` variants; 8(e): hdiff / vadv column shards).
+ *      The reference is single device; NPBench's harness is one process, so sharding that needs no exchange is driven
+ *      from that one process: slot 0 is npb_init's device, npb_mg_init(n, devices) makes slot k drive devices[k]
+ *      (a device may repeat).  npb_mg_select(k) redirects every following call (allocator, copies, kernels, timers)
+ *      to slot k; select 0 to return.  NPBench reaches this with NPB_B200_GPUS=N (plugin: scatter in setup_str,
+ *      framework.py:139-150; gather in copy_back_func). */
+int npb_mg_init(int ndev, const int *devices);
+int npb_mg_count(void);
+int npb_mg_select(int slot);
+int npb_mg_current(void);
+int npb_shard_bounds(int64_t n, int nshards, int s, int64_t *lo, int64_t *hi);   /* rows [lo, hi) of shard s */
+/* hdiff split along I: shard s = output rows [i_lo[s], i_lo[s+1]) on slot slots[s]; in_shards[s] holds in_field rows
+ * [i_lo[s], i_lo[s+1] + 4) (fixed 4-row overlap, hdiff_numpy.py:7-28); i_lo has nshards + 1 entries, 0 .. I */
+int npb_hdiff_f64_mg(int nshards, const int *slots, int64_t I, int64_t J, int64_t K,
+                     const double *const *in_shards, double *const *out_shards,
+                     const double *const *coeff_shards, const int64_t *i_lo);
+/* vadv split along I: wcon_shards[s] holds wcon rows [i_lo[s], i_lo[s+1] + 1) (vadv_numpy.py:16, 33-34) */
+int npb_vadv_f64_mg(int nshards, const int *slots, int64_t I, int64_t J, int64_t K,
+                    double *const *utens_stage, const double *const *u_stage, const double *const *wcon_shards,
+                    const double *const *u_pos, const double *const *utens, double dtr_stage, const int64_t *i_lo);
+/* the same on HOST buffers with the NumPy signatures' array layout: scatter, run, gather, synchronise;
+ * shard s runs on slot s % npb_mg_count() */
+int npb_hdiff_f64_mg_host(int nshards, int64_t I, int64_t J, int64_t K, const double *in_field,
+                          double *out_field, const double *coeff);
+int npb_vadv_f64_mg_host(int nshards, int64_t I, int64_t J, int64_t K, double *utens_stage, const double *u_stage,
+                         const double *wcon, const double *u_pos, const double *utens, double dtr_stage);
 
 /* ---- device memory: what Framework.copy_func / copy_back_func need
  *      (framework.py:42-50; called once per array per repetition,

@@ -8,6 +8,7 @@ this package is the thin ctypes host side plus the NPBench plugin files
 """
 from ._lib import B200Error, init, lib  # noqa: F401
 from .device_array import DeviceArray  # noqa: F401
+from .sharded import ShardedArray  # noqa: F401
 from .kernels import adi, cavity_flow, channel_flow, fdtd_2d, hdiff, heat_3d, jacobi_1d, jacobi_2d, seidel_2d, sync, vadv  # noqa: F401
 
 __version__ = "0.1.0"

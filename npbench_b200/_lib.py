@@ -25,6 +25,17 @@ PROTOTYPES = {
     "npb_set_stream": (_int, [_vp]),
     "npb_get_stream": (_vp, []),
     "npb_sync": (_int, []),
+    "npb_mg_init": (_int, [_int, ctypes.POINTER(_int)]),
+    "npb_mg_count": (_int, []),
+    "npb_mg_select": (_int, [_int]),
+    "npb_mg_current": (_int, []),
+    "npb_shard_bounds": (_int, [_i64, _int, _int, ctypes.POINTER(_i64), ctypes.POINTER(_i64)]),
+    "npb_hdiff_f64_mg": (_int, [_int, ctypes.POINTER(_int), _i64, _i64, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                ctypes.POINTER(_vp), ctypes.POINTER(_i64)]),
+    "npb_vadv_f64_mg": (_int, [_int, ctypes.POINTER(_int), _i64, _i64, _i64] + [ctypes.POINTER(_vp)] * 5 +
+                        [_dbl, ctypes.POINTER(_i64)]),
+    "npb_hdiff_f64_mg_host": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "npb_vadv_f64_mg_host": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _dbl]),
     "npb_malloc": (_int, [_sz, ctypes.POINTER(_vp)]),
     "npb_free": (_int, [_vp]),
     "npb_pool_trim": (_int, []),
@@ -84,7 +95,7 @@ PROTOTYPES = {
     "npb_init_fdtd2d_f64": (_int, [_i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 
-_NO_STATUS = {"npb_version", "npb_last_error", "npb_get_stream", "npb_launch_count",
+_NO_STATUS = {"npb_version", "npb_last_error", "npb_get_stream", "npb_launch_count", "npb_mg_count", "npb_mg_current",
               "npb_jacobi2d_tile_rows", "npb_jacobi2d_last_path", "npb_seidel2d_last_path", "npb_heat3d_last_path", "npb_fdtd2d_last_path", "npb_fdtd2d_pass_plan", "npb_hdiff_last_path", "npb_vadv_last_path"}
 
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnpb_b200.so")
 SOURCES = ["runtime.cu", "host_api.cu", "init_fields.cu", "jacobi2d.cu", "heat3d.cu", "fdtd2d.cu",
-           "hdiff.cu", "vadv.cu", "vadv_stream.cu", "jacobi1d.cu", "seidel2d.cu", "adi.cu", "cavity_flow.cu", "channel_flow.cu"]
+           "hdiff.cu", "vadv.cu", "vadv_stream.cu", "jacobi1d.cu", "seidel2d.cu", "adi.cu", "cavity_flow.cu", "channel_flow.cu", "multi_device.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-O2",

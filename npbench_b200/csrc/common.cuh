@@ -7,6 +7,8 @@
 
 #include "../../include/npb_b200.h"
 
+#define NPB_MAX_DEVICES 16
+
 namespace npb {
 
 struct State {
@@ -19,10 +21,10 @@ struct State {
     cudaStream_t stream = nullptr;       // the stream kernels are enqueued on
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint64_t launches = 0;
-    char err[512] = {0};
 };
 
-State &st();
+State &st();          // state of the CURRENT device slot (slot 0 unless npb_mg_select changed it)
+int cur_slot();
 int fail(const char *where, const char *msg);
 int fail_cuda(const char *where, cudaError_t e);
 

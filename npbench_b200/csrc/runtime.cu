@@ -11,16 +11,23 @@
 
 namespace npb {
 
-static State g_state;
-State &st() { return g_state; }
+// One State per device slot.  Slot 0 is the device npb_init selected (the one GPU of a normal, one-process-per-GPU
+// run); npb_mg_init adds slots for the single-process multi-device entry points (npb_hdiff_f64_mg / npb_vadv_f64_mg:
+// column shards need no exchange, so one process can drive all GPUs).  st() is the state of the CURRENT slot; every
+// kernel launcher goes through it, so selecting a slot redirects stream, workspaces, allocator and graph cache.
+static State g_states[NPB_MAX_DEVICES];
+static int g_cur = 0, g_nslots = 1;
+static char g_err[512] = {0};
+State &st() { return g_states[g_cur]; }
+int cur_slot() { return g_cur; }
 
 int fail(const char *where, const char *msg) {
-    snprintf(g_state.err, sizeof(g_state.err), "%s: %s", where, msg);
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, msg);
     return 1;
 }
 
 int fail_cuda(const char *where, cudaError_t e) {
-    snprintf(g_state.err, sizeof(g_state.err), "%s: CUDA error %d (%s)", where, (int)e,
+    snprintf(g_err, sizeof(g_err), "%s: CUDA error %d (%s)", where, (int)e,
              cudaGetErrorString(e));
     cudaGetLastError();  // clear the sticky "last error" slot for non-fatal failures
     return (int)e ? (int)e : 1;
@@ -36,7 +43,8 @@ struct Pool {
     std::unordered_map<void *, size_t> live;         // block -> rounded size
     size_t cached_bytes = 0;
 };
-static Pool g_pool;
+static Pool g_pools[NPB_MAX_DEVICES];
+#define g_pool (g_pools[g_cur])
 
 static size_t round_size(size_t b) {
     const size_t g = b < (1u << 20) ? 512 : (size_t)(2u << 20);
@@ -44,7 +52,8 @@ static size_t round_size(size_t b) {
 }
 
 struct Workspace { void *p = nullptr; size_t bytes = 0; };
-static Workspace g_ws[8];
+static Workspace g_ws_all[NPB_MAX_DEVICES][8];
+#define g_ws (g_ws_all[g_cur])
 
 void *workspace(int slot, size_t bytes) {
     Workspace &w = g_ws[slot];
@@ -58,6 +67,7 @@ void *workspace(int slot, size_t bytes) {
 // ---- CUDA-graph cache ------------------------------------------------------
 struct GraphEntry {
     GraphKey key;
+    int slot = 0;              // device slot the graph was captured on
     cudaGraphExec_t exec = nullptr;
     uint64_t launches = 0;     // kernels inside the graph (for npb_launch_count)
     uint64_t stamp = 0;        // LRU
@@ -70,7 +80,7 @@ static bool same_key(const GraphKey &a, const GraphKey &b) { return memcmp(&a, &
 
 bool graph_replay(const GraphKey &key) {
     for (auto &e : g_graphs)
-        if (e.exec && same_key(e.key, key)) {
+        if (e.exec && e.slot == g_cur && same_key(e.key, key)) {
             if (cudaGraphLaunch(e.exec, st().stream) != cudaSuccess) { cudaGetLastError(); return false; }
             e.stamp = ++g_graph_clock;
             st().launches += e.launches;
@@ -112,6 +122,7 @@ int graph_end_and_launch(const GraphKey &key, int rc) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { slot->exec = nullptr; return fail_cuda("cudaGraphInstantiate", e); }
     slot->key = key;
+    slot->slot = g_cur;
     slot->launches = st().launches - g_capture_launch_base;          // counted while capturing
     slot->stamp = ++g_graph_clock;
     e = cudaGraphLaunch(slot->exec, st().stream);
@@ -126,18 +137,9 @@ using namespace npb;
 extern "C" {
 
 const char *npb_version(void) { return "0.1.0"; }
-const char *npb_last_error(void) { return st().err; }
+const char *npb_last_error(void) { return g_err; }
 
-int npb_init(int device) {
-    State &s = st();
-    if (s.inited && (device < 0 || device == s.device)) return 0;
-    if (s.inited) return fail("npb_init", "already initialised on another device (one GPU per process)");
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0)
-        return fail("npb_init", "no CUDA device visible: libnpb_b200 has no CPU fallback");
-    if (device < 0) device = 0;
-    if (device >= n) return fail("npb_init", "device index out of range");
+static int init_slot(State &s, int device) {
     NPB_CUDA(cudaSetDevice(device));
     cudaDeviceProp p;
     NPB_CUDA(cudaGetDeviceProperties(&p, device));
@@ -155,18 +157,72 @@ int npb_init(int device) {
     return 0;
 }
 
+int npb_init(int device) {
+    State &s = g_states[0];
+    if (s.inited && (device < 0 || device == s.device)) return 0;
+    if (s.inited) return fail("npb_init", "already initialised on another device (one GPU per process)");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail("npb_init", "no CUDA device visible: libnpb_b200 has no CPU fallback");
+    if (device < 0) device = 0;
+    if (device >= n) return fail("npb_init", "device index out of range");
+    g_cur = 0;
+    return init_slot(s, device);
+}
+
 int npb_shutdown(void) {
-    State &s = st();
-    if (!s.inited) return 0;
-    cudaDeviceSynchronize();
-    npb_pool_trim();
-    for (auto &w : g_ws) { if (w.p) cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
-    for (auto &g : g_graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    cudaEventDestroy(s.ev0); cudaEventDestroy(s.ev1);
-    cudaStreamDestroy(s.own_stream);
-    s = State();
+    for (int k = g_nslots - 1; k >= 0; --k) {
+        State &s = g_states[k];
+        if (!s.inited) continue;
+        g_cur = k;
+        cudaSetDevice(s.device);
+        cudaDeviceSynchronize();
+        npb_pool_trim();
+        for (auto &w : g_ws) { if (w.p) cudaFree(w.p); w.p = nullptr; w.bytes = 0; }
+        for (auto &g : g_graphs) { if (g.exec && g.slot == k) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } }
+        cudaEventDestroy(s.ev0); cudaEventDestroy(s.ev1);
+        cudaStreamDestroy(s.own_stream);
+        s = State();
+    }
+    g_cur = 0; g_nslots = 1;
     return 0;
 }
+
+// ---- single-process multi-device plumbing (column-sharded hdiff / vadv: no exchange, so no NCCL) ----------------
+// Slot 0 is npb_init's device.  npb_mg_init(n, devices) makes sure slot k drives devices[k] for k < n (devices[0]
+// must be slot 0's device or slot 0 must be uninitialised); a device may appear more than once (shards that share
+// a GPU -- how the one-GPU test box exercises this path).  Returns 0 or an error code.
+int npb_mg_init(int ndev, const int *devices) {
+    NPB_ARG(ndev >= 1 && ndev <= NPB_MAX_DEVICES && devices != nullptr, "npb_mg_init", "1..16 devices");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+        return fail("npb_mg_init", "no CUDA device visible: libnpb_b200 has no CPU fallback");
+    for (int k = 0; k < ndev; ++k)
+        NPB_ARG(devices[k] >= 0 && devices[k] < n, "npb_mg_init", "device index out of range");
+    if (!g_states[0].inited) { const int rc = npb_init(devices[0]); if (rc) return rc; }
+    NPB_ARG(g_states[0].device == devices[0], "npb_mg_init", "devices[0] must be the device npb_init selected");
+    for (int k = 1; k < ndev; ++k) {
+        State &s = g_states[k];
+        if (s.inited && s.device == devices[k]) continue;
+        NPB_ARG(!s.inited, "npb_mg_init", "slot already drives another device");
+        const int rc = init_slot(s, devices[k]);
+        if (rc) { cudaSetDevice(g_states[0].device); return rc; }
+    }
+    if (ndev > g_nslots) g_nslots = ndev;
+    g_cur = 0;
+    NPB_CUDA(cudaSetDevice(g_states[0].device));
+    return 0;
+}
+int npb_mg_count(void) { return g_nslots; }
+// make slot k current (stream, allocator, workspaces, graph cache follow); k = 0 returns to the primary device
+int npb_mg_select(int slot) {
+    NPB_ARG(slot >= 0 && slot < g_nslots && g_states[slot].inited, "npb_mg_select", "slot not initialised");
+    g_cur = slot;
+    NPB_CUDA(cudaSetDevice(g_states[slot].device));
+    return 0;
+}
+int npb_mg_current(void) { return g_cur; }
 
 int npb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_bytes,
                     size_t *smem_per_block_optin, size_t *total_mem) {
@@ -191,7 +247,17 @@ void *npb_get_stream(void) { return (void *)st().stream; }
 
 int npb_sync(void) {
     NPB_REQUIRE_INIT();
-    NPB_CUDA(cudaStreamSynchronize(st().stream));
+    if (g_nslots == 1) {
+        NPB_CUDA(cudaStreamSynchronize(st().stream));
+        return 0;
+    }
+    const int keep = g_cur;                     // every device this process drives
+    for (int k = 0; k < g_nslots; ++k) {
+        if (!g_states[k].inited) continue;
+        NPB_CUDA(cudaSetDevice(g_states[k].device));
+        NPB_CUDA(cudaStreamSynchronize(g_states[k].stream));
+    }
+    NPB_CUDA(cudaSetDevice(g_states[keep].device));
     return 0;
 }
 
@@ -226,15 +292,19 @@ int npb_malloc(size_t bytes, void **dptr) {
 
 int npb_free(void *dptr) {
     if (!dptr) return 0;
-    std::lock_guard<std::mutex> lk(g_pool.mu);
-    auto it = g_pool.live.find(dptr);
-    if (it == g_pool.live.end()) return fail("npb_free", "pointer was not allocated by npb_malloc");
-    // Stream-ordered reuse: every consumer of this library enqueues on one
-    // stream, so a recycled block is only touched after earlier work on it.
-    g_pool.free_blocks.emplace(it->second, dptr);
-    g_pool.cached_bytes += it->second;
-    g_pool.live.erase(it);
-    return 0;
+    for (int k = 0; k < g_nslots; ++k) {            // the block goes back to the pool of the slot that allocated it
+        Pool &pool = g_pools[k];
+        std::lock_guard<std::mutex> lk(pool.mu);
+        auto it = pool.live.find(dptr);
+        if (it == pool.live.end()) continue;
+        // Stream-ordered reuse: every consumer of this library enqueues on one
+        // stream per device, so a recycled block is only touched after earlier work on it.
+        pool.free_blocks.emplace(it->second, dptr);
+        pool.cached_bytes += it->second;
+        pool.live.erase(it);
+        return 0;
+    }
+    return fail("npb_free", "pointer was not allocated by npb_malloc");
 }
 
 int npb_pool_trim(void) {

@@ -64,6 +64,9 @@ def fdtd_2d(TMAX, ex, ey, hz, _fict_):
 
 def hdiff(in_field, out_field, coeff):
     """hdiff(in_field, out_field, coeff) -- weather_stencils/hdiff/hdiff_numpy.py:5-29."""
+    from .sharded import ShardedArray, hdiff_mg
+    if isinstance(out_field, ShardedArray):            # NPB_B200_GPUS > 1: column shards, one process, no exchange
+        return hdiff_mg(in_field, out_field, coeff)
     I, J, K = out_field.shape
     if tuple(in_field.shape) != (I + 4, J + 4, K) or tuple(coeff.shape) != (I, J, K):
         raise ValueError("expected in_field (I+4,J+4,K), out_field/coeff (I,J,K)")
@@ -74,6 +77,9 @@ def hdiff(in_field, out_field, coeff):
 
 def vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage):
     """vadv(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage) -- vadv_numpy.py:9-78."""
+    from .sharded import ShardedArray, vadv_mg
+    if isinstance(utens_stage, ShardedArray):
+        return vadv_mg(utens_stage, u_stage, wcon, u_pos, utens, dtr_stage)
     I, J, K = utens_stage.shape
     if tuple(wcon.shape) != (I + 1, J, K):
         raise ValueError("wcon must be (I+1, J, K)")

@@ -12,7 +12,8 @@ from typing import Any, Callable, Dict
 from npbench.infrastructure import Benchmark, Framework
 
 import npbench_b200
-from npbench_b200 import DeviceArray
+from npbench_b200 import DeviceArray, ShardedArray
+from npbench_b200 import sharded as _sharded
 
 __all__ = ["B200Framework"]
 
@@ -25,8 +26,12 @@ def _to_device(a):
 
 
 def _to_host(a):
-    """copy_back_func: outputs back to NumPy for util.validate (test.py:107-110)."""
-    return a.to_host() if isinstance(a, DeviceArray) else a
+    """copy_back_func: outputs back to NumPy for util.validate (test.py:107-110); gathers column shards."""
+    return a.to_host() if isinstance(a, (DeviceArray, ShardedArray)) else a
+
+
+# benchmarks whose array arguments are scattered over NPB_B200_GPUS devices (no run-time exchange needed)
+_SHARDED_BENCHES = {"hdiff", "vadv"}
 
 
 class B200Framework(Framework):
@@ -35,8 +40,10 @@ class B200Framework(Framework):
     def __init__(self, fname: str):
         super().__init__(fname)
         import os
-        # one GPU per process; fails loudly when no B200 is visible (no CPU fallback)
+        # fails loudly when no B200 is visible (no CPU fallback).  NPB_B200_GPUS = N > 1: hdiff and vadv are split
+        # along I over N device slots of this one process (npbench_b200/sharded.py); everything else runs on device 0
         npbench_b200.init(int(os.environ.get("NPB_B200_DEVICE", "0")))
+        self.devices = _sharded.configure(_sharded.devices_from_env())
 
     def version(self) -> str:
         # the base class asks pkg_resources for a distribution called "b200" (framework.py:33-35)
@@ -44,7 +51,7 @@ class B200Framework(Framework):
 
     def imports(self) -> Dict[str, Any]:
         # merged into the exec namespace (test.py:90)
-        return {"__npb_b200_sync": npbench_b200.sync}
+        return {"__npb_b200_sync": npbench_b200.sync, "__npb_b200_scatter": _sharded.scatter}
 
     def copy_func(self) -> Callable:
         return _to_device
@@ -54,6 +61,13 @@ class B200Framework(Framework):
 
     def setup_str(self, bench: Benchmark, impl: Callable = None) -> str:
         # H2D copies finish before the timer starts (cupy_framework.py:32-45)
+        name = bench.info["module_name"]
+        if len(self.devices) > 1 and name in _SHARDED_BENCHES and len(bench.info["array_args"]):
+            # copy_func only sees the array (framework.py:149), but in_field / wcon need their row overlap: emit one
+            # scatter call per array argument that names the benchmark and the argument (framework.py:139-150)
+            arg_str = self.out_arg_str(bench, impl)
+            calls = ", ".join("__npb_b200_scatter({a}, '{b}', '{a}')".format(a=a, b=name) for a in bench.info["array_args"])
+            return arg_str + " = " + calls + "; " + _SYNC
         base = super().setup_str(bench, impl)
         return _SYNC if base == "pass" else base + "; " + _SYNC
 

@@ -107,3 +107,12 @@ def test_real_harness_b200_paper(bench, tmp_path):
 @pytest.mark.parametrize("bench", ["jacobi_1d", "seidel_2d", "adi", "cavity_flow", "channel_flow"])
 def test_real_harness_b200_widening_row(bench, tmp_path):
     _check_b200_run(tmp_path, bench, "S", 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bench,preset", [("hdiff", "S"), ("hdiff", "paper"), ("vadv", "M")])
+def test_real_harness_b200_column_shards(bench, preset, tmp_path, monkeypatch):
+    """BASELINE.json configs[2]: hdiff `paper` column-sharded, reached through the UNMODIFIED harness with
+    NPB_B200_GPUS=N (one process, N device slots; on a one-GPU box the slots share device 0)."""
+    monkeypatch.setenv("NPB_B200_GPUS", "3")
+    _check_b200_run(tmp_path, bench, preset, 2)
