@@ -426,7 +426,7 @@ extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const 
     NPB_ARG(nj - 2 < (int64_t)TileBig::TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
     if (ni < 3 || nj < 3) return 0;   // no interior
     // big slabs: the same rows by marching passes (tile rows -> interior rows [1 + lo*TI, 1 + hi*TI))
-    if (nsteps >= 3 && nj >= 8 &&
+    if (nj >= 8 &&
         (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP))) {
         const int64_t tiles_i = (ni - 2 + TileBig::TI - 1) / TileBig::TI;
         if (tile_row_hi < 0 || tile_row_hi > tiles_i) tile_row_hi = tiles_i;
@@ -473,12 +473,12 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
         if (take > cap) take = cap;
         extra_pairs -= take;
         const int ns = (int)(1 + 2 * take);
-        if (march && ns >= 3) rc = launch_jm(ns, ni, nj, src, dst, g_jacobi_rc);
+        if (march) rc = launch_jm(ns, ni, nj, src, dst, g_jacobi_rc);
         else rc = launch_block(tile, ns, ni, nj, src, dst, 0, -1);
         double *t = src; src = dst; dst = t;
     }
     // now src == B (state S-1), dst == A
-    if (!rc) rc = launch_block(tile, 1, ni, nj, src, dst, 0, -1);
+    if (!rc) rc = march ? launch_jm(1, ni, nj, src, dst, g_jacobi_rc) : launch_block(tile, 1, ni, nj, src, dst, 0, -1);
     if (capturing) {
         const int rc2 = npb::graph_end_and_launch(key, rc);
         if (!rc) rc = rc2;

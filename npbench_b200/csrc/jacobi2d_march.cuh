@@ -303,7 +303,7 @@ int launch_jm_ns(const JmParams &p, dim3 grid, bool vec) {
     return 0;
 }
 
-// one pass: ns (3, 5 or 7) sweeps src -> dst
+// one pass: ns (1, 3, 5 or 7) sweeps src -> dst
 int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, int rc_override, int64_t row_lo = 0,
               int64_t row_hi = -1) {
     if (row_hi < 0 || row_hi > ni) row_hi = ni;
@@ -325,6 +325,7 @@ int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, in
     JmParams p{ni, nj, nstrips, row_lo, row_hi, (int)rc, pfd, src, dst};
     dim3 grid((unsigned)blocks_x, (unsigned)chunks);
     switch (ns) {
+        case 1: return launch_jm_ns<1>(p, grid, vec);     // the closing single sweep of a big grid: a plain HBM stream
         case 3: return launch_jm_ns<3>(p, grid, vec);
         case 5: return launch_jm_ns<5>(p, grid, vec);
         case 7: return launch_jm_ns<7>(p, grid, vec);
