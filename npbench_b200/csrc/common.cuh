@@ -25,6 +25,7 @@ struct State {
 
 State &st();          // state of the CURRENT device slot (slot 0 unless npb_mg_select changed it)
 int cur_slot();
+int cur_device();     // CUDA ordinal of the current slot's device, < NPB_MAX_DEVICES (function attributes are per device)
 int fail(const char *where, const char *msg);
 int fail_cuda(const char *where, cudaError_t e);
 

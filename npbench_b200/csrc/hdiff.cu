@@ -318,9 +318,9 @@ int try_ring(int64_t I, int64_t J, int64_t K, const double *in, double *out, con
     ring::Params rp{(int)I, (int)J, (int)K, TJ, n_jtiles, RB, n_iblocks, slot_in, slot_elems, in, out, coeff};
     const long long units = (long long)n_iblocks * n_jtiles;
     const int grid = (int)(units < sms ? units : sms);
-    // function attributes are per device: one cache per device slot (npb_mg_select)
+    // function attributes are per device: one cache per device (npb_mg_select)
     static size_t cfg8[NPB_MAX_DEVICES] = {0}, cfg4[NPB_MAX_DEVICES] = {0};
-    size_t &configured8 = cfg8[npb::cur_slot()], &configured4 = cfg4[npb::cur_slot()];
+    size_t &configured8 = cfg8[npb::cur_device()], &configured4 = cfg4[npb::cur_device()];
     if (n_slots == 8) {
         if (smem > configured8) {
             if (cudaFuncSetAttribute(ring::hdiff_ring_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

@@ -42,6 +42,9 @@ struct JacobiTile {
 using TileBig = JacobiTile<128, 32>;     // 46 x 128 region, 94 KB, 2 CTAs/SM
 using TileMid = JacobiTile<128, 16>;     // 30 x 128 region, 61 KB
 using TileSmall = JacobiTile<64, 8>;     // 22 x 64 region, 22 KB
+using Tile24 = JacobiTile<128, 24>;      // in-between heights: chosen when they avoid a nearly empty second wave
+using Tile20 = JacobiTile<128, 20>;      // (700^2: 308 tiles of 16 rows on 296 CTA slots vs 245 tiles of 20 rows)
+using Tile12 = JacobiTile<128, 12>;
 
 template <class T>
 __global__ void __launch_bounds__(JB_THREADS, 2)
@@ -386,20 +389,34 @@ int launch_block_t(int nsteps, int64_t ni, int64_t nj, const double *src, double
     return 0;
 }
 
-// tile choice for whole-grid passes: the largest tile that still gives every SM ~2 CTAs
+// tile choice for whole-grid passes.  A pass is one wave of CTAs when it can be: the small tile if all its CTAs are
+// co-resident (3 per SM), else the LOWEST 128-column tile whose CTAs fit the 2-per-SM slots (most CTAs in flight, no
+// nearly empty second wave: 700^2 is 308 tiles of 16 rows on 296 slots but 245 tiles of 20 rows -- measured 1.12 ms vs
+// 0.87 ms per call), else the big tile (least halo redundancy once there are many waves anyway).
+// Measured at S / M / L / paper: small, small, 20 rows, big are the fastest of the six.
 int pick_tile(int64_t ni, int64_t nj) {
-    const int64_t want = 2LL * npb::st().sm_count;
-    auto tiles = [&](int ti, int tj) { return ((ni - 2 + ti - 1) / ti) * ((nj - 2 + tj - 1) / tj); };
-    if (tiles(TileBig::TI, TileBig::TJ) >= want) return 0;
-    if (tiles(TileMid::TI, TileMid::TJ) >= want) return 1;
-    return 2;
+    const int64_t sms = npb::st().sm_count;
+    static const int forced = getenv("NPB_J2_TILE") ? atoi(getenv("NPB_J2_TILE")) : -1;
+    if (forced >= 0 && forced <= 5) return forced;
+    auto ctas = [&](int ti, int tj) { return ((ni - 2 + ti - 1) / ti) * ((nj - 2 + tj - 1) / tj); };
+    if (ctas(TileSmall::TI, TileSmall::TJ) <= 3 * sms) return 2;
+    if (ctas(Tile12::TI, Tile12::TJ) <= 2 * sms) return 5;
+    if (ctas(TileMid::TI, TileMid::TJ) <= 2 * sms) return 1;
+    if (ctas(Tile20::TI, Tile20::TJ) <= 2 * sms) return 4;
+    if (ctas(Tile24::TI, Tile24::TJ) <= 2 * sms) return 3;
+    return 0;
 }
 
 int launch_block(int tile, int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, int64_t tr_lo,
                  int64_t tr_hi) {
-    if (tile == 0) return launch_block_t<TileBig>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
-    if (tile == 1) return launch_block_t<TileMid>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
-    return launch_block_t<TileSmall>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+    switch (tile) {
+        case 0: return launch_block_t<TileBig>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+        case 1: return launch_block_t<TileMid>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+        case 3: return launch_block_t<Tile24>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+        case 4: return launch_block_t<Tile20>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+        case 5: return launch_block_t<Tile12>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+        default: return launch_block_t<TileSmall>(nsteps, ni, nj, src, dst, tr_lo, tr_hi);
+    }
 }
 
 }  // namespace

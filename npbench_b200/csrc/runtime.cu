@@ -20,6 +20,7 @@ static int g_cur = 0, g_nslots = 1;
 static char g_err[512] = {0};
 State &st() { return g_states[g_cur]; }
 int cur_slot() { return g_cur; }
+int cur_device() { return g_states[g_cur].device & (NPB_MAX_DEVICES - 1); }
 
 int fail(const char *where, const char *msg) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, msg);

@@ -568,8 +568,8 @@ extern "C" int npb_vadv_f64(int64_t I, int64_t J, int64_t K, double *utens_stage
     NPB_ARG(pick_geometry((int)K, npb::st().smem_optin, &ntiles, &NC, &NCP, &bytes), "npb_vadv_f64",
             "K too large for the shared-memory column tile");
     g_vadv_last = use_tma ? 2 : 1;
-    static size_t cfg[NPB_MAX_DEVICES] = {0}, cfg_tma[NPB_MAX_DEVICES] = {0};      // per device slot
-    size_t &configured = cfg[npb::cur_slot()], &configured_tma = cfg_tma[npb::cur_slot()];
+    static size_t cfg[NPB_MAX_DEVICES] = {0}, cfg_tma[NPB_MAX_DEVICES] = {0};      // per device
+    size_t &configured = cfg[npb::cur_device()], &configured_tma = cfg_tma[npb::cur_device()];
     if (!use_tma && bytes > configured) {
         NPB_CUDA(cudaFuncSetAttribute(vadv_pipeline_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = bytes;
