@@ -464,8 +464,8 @@ def record_kernel_name(L, bench):
         return {1: "heat3d_resident_kernel", 2: "heat3d_sweep_kernel", 5: "heat3d_march_kernel",
                 6: "heat3d_regtile_kernel"}.get(int(L.heat3d_last_path()), "heat3d")
     if bench == "jacobi_2d":
-        return {1: "jacobi2d_resident_kernel", 2: "jacobi2d_block_kernel", 3: "jacobi2d_march_kernel",
-                4: "jacobi2d_regtile_kernel"}.get(int(L.jacobi2d_last_path()), "jacobi2d")
+        return {1: "jacobi2d_regtile_kernel", 2: "jacobi2d_block_kernel", 3: "jacobi2d_march_kernel"}.get(
+            int(L.jacobi2d_last_path()), "jacobi2d")
     if bench == "hdiff":
         return {1: "hdiff_march_kernel", 2: "hdiff_ring_kernel"}.get(int(L.hdiff_last_path()), "hdiff")
     return {1: "vadv_pipeline_kernel", 2: "vadv_tma_kernel", 3: "vadv_stream_kernel (TMEM + TMA streaming Thomas solver)"}.get(

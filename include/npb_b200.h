@@ -110,11 +110,16 @@ int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *
 #define NPB_JACOBI2D_MAX_BLOCK 7
 int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst,
                            int64_t tile_row_lo, int64_t tile_row_hi);
-/* mode & 7: 0 dispatch by size (grids of >= 14M cells: marching passes, jacobi2d_march_kernel, 3/5/7 sweeps per
- * pass in registers; else blocked shared-memory passes), 1 blocked passes, 2 on-chip resident kernel when eligible
- * (opt-in), 3 marching passes at any size (nj >= 8); mode >> 8 = rows per chunk of the marching kernel (0 = auto) */
+/* mode & 7: 0 dispatch by size (grids that fit on chip -- NPBench S / M / L -- run in ONE cooperative launch:
+ * jacobi2d_regtile_kernel, cell state in registers, T sweeps per halo exchange through in-L2 inboxes; grids of
+ * >= 14M cells: marching passes, jacobi2d_march_kernel, 3/5/7 sweeps per pass in registers; else blocked
+ * shared-memory passes), 1 blocked passes, 2 same as 0, 3 marching passes at any size (nj >= 8);
+ * mode >> 8 = rows per chunk of the marching kernel (0 = auto) */
 int npb_jacobi2d_set_mode(int mode);
-int npb_jacobi2d_last_path(void);        /* 1 resident, 2 blocked passes, 3 marching passes */
+int npb_jacobi2d_last_path(void);        /* 1 register-tile resident kernel, 2 blocked passes, 3 marching passes */
+/* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, sweeps per
+ * halo exchange, tiles along i, tiles along j, CTAs per SM} */
+int npb_jacobi2d_regtile_config(int *out7);
 int npb_jacobi2d_tile_rows(void);        /* rows per tile of the blocked kernel */
 
 /* kernel(TSTEPS, A, B): polybench/heat_3d/heat_3d_numpy.py:4-20.  (n0,n1,n2). */

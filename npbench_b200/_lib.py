@@ -53,6 +53,7 @@ PROTOTYPES = {
     "npb_jacobi2d_block_f64": (_int, [_int, _i64, _i64, _vp, _vp, _i64, _i64]),
     "npb_jacobi2d_set_mode": (_int, [_int]),
     "npb_jacobi2d_last_path": (_int, []),
+    "npb_jacobi2d_regtile_config": (_int, [_vp]),
     "npb_jacobi2d_tile_rows": (_int, []),
     "npb_heat3d_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp]),
     "npb_fdtd2d_set_mode": (_int, [_int]),
