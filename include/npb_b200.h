@@ -149,11 +149,16 @@ int npb_heat3d_sweep_f64(int64_t n0, int64_t n1, int64_t n2, const double *src, 
 /* kernel(TMAX, ex, ey, hz, _fict_): polybench/fdtd_2d/fdtd_2d_numpy.py:4-11. */
 int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz,
                    const double *fict);
-/* mode & 3: 0 = dispatch by size (grids of >= 4M cells: marching passes of up to four time steps,
- * fdtd2d_march_kernel; else one launch per step), 1 = always one launch per step, 2 = marching
- * passes at any size (TMAX >= 2); mode >> 8 = rows per chunk of the marching kernel (0 = automatic). */
+/* mode & 3: 0 = dispatch by size (grids that fit on chip -- NPBench S / M / L -- run in ONE cooperative launch:
+ * fdtd2d_regtile_kernel, the three fields in registers, T steps per halo exchange through in-L2 inboxes; grids of
+ * >= 4M cells: marching passes of up to five time steps, fdtd2d_march_kernel; else one launch per step),
+ * 1 = always one launch per step, 2 = marching passes at any size (TMAX >= 2), 3 = same as 0;
+ * mode >> 8 = rows per chunk of the marching kernel (0 = automatic). */
 int npb_fdtd2d_set_mode(int mode);
-int npb_fdtd2d_last_path(void);          /* last call: 1 one launch per step, 2 marching passes */
+int npb_fdtd2d_last_path(void);          /* last call: 1 one launch per step, 2 marching passes, 3 register-tile resident kernel */
+/* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, steps per
+ * halo exchange, tiles along i, tiles along j} */
+int npb_fdtd2d_regtile_config(int *out6);
 /* host logic only: the steps-per-pass plan of npb_fdtd2d_f64 (march != 0: up to five steps per pass, an even
  * number of passes when TMAX allows); writes min(passes, cap) entries, returns the number of passes */
 int npb_fdtd2d_pass_plan(int64_t tmax, int march, int32_t *steps, int cap);

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "npb_heat3d_f64": (_int, [_i64, _i64, _i64, _i64, _vp, _vp]),
     "npb_fdtd2d_set_mode": (_int, [_int]),
     "npb_fdtd2d_last_path": (_int, []),
+    "npb_fdtd2d_regtile_config": (_int, [_vp]),
     "npb_fdtd2d_pass_plan": (_int, [_i64, _int, _vp, _int]),
     "npb_heat3d_set_mode": (_int, [_int]),
     "npb_heat3d_last_path": (_int, []),

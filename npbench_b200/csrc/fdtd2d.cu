@@ -14,7 +14,10 @@
 // driver (rows whose stencil leaves the slab are ghost rows: copied).
 //
 // Arithmetic in NumPy order, -fmad=false (oracle: npb_oracle_fdtd2d).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+#include "inbox.cuh"
 
 namespace {
 
@@ -93,14 +96,127 @@ void fdtd_plan(int64_t tmax, bool march, int64_t *passes, int64_t *base, int64_t
     *rem = n ? tmax % n : 0;
 }
 
-int g_fd_mode = 0;      // 0 dispatch by size, 1 one launch per step, 2 marching passes whenever TMAX >= 2
+int g_fd_mode = 0;      // 0 dispatch by size, 1 one launch per step, 2 marching passes whenever TMAX >= 2, 3 = 0
 int g_fd_rc = 0;        // rows per chunk override for the marching kernel (0 = automatic)
-int g_fd_last = 0;      // 1 one launch per step, 2 marching passes
+int g_fd_last = 0;      // 1 one launch per step, 2 marching passes, 3 register-tile resident kernel
+
+#include "fdtd2d_regtile.cuh"
+
+// ---- register-tile resident kernel (fdtd2d_regtile.cuh): configuration, inbox arming, cooperative launch ----
+struct F2Config { int rb, cb, nw, T, PI, PJ; };
+struct F2Armed { unsigned long long *box = nullptr; size_t words = 0; int geo[8] = {0, 0, 0, 0, 0, 0, 0, 0}; };
+F2Armed g_f2_armed;
+F2Config g_f2_last = {0, 0, 0, 0, 0, 0};
+
+// Modelled microseconds per step (see j2_cost in jacobi2d.cu for the measurements behind the constants): per warp
+// and step the MIO pipe moves 2 RB 64-bit shuffles (old hz from the left lane, new ex from the right one) and six
+// rows of CB doubles through shared memory; the FP64 pipe 11 operations per cell + 3 per recomputed edge cell.
+double f2_cost(const F2Config &c) {
+    const double cells = (double)c.rb * c.cb;
+    const double mio = 4.0 * c.rb + 12.0 * c.cb, fp64 = (11.0 * cells + 3.0 * c.cb) / 2.0;
+    const double per_warp = 1.15 * (mio > fp64 ? mio : fp64) / 1965.0;
+    const double step = 0.20 + 0.02 * cells + c.nw * per_warp;
+    const double exchange = (c.PI * c.PJ > 1) ? 2.6 : 0.0;
+    return step + exchange / c.T;
+}
+
+bool f2_tiles(int64_t nx, int64_t ny, int sms, F2Config &c) {
+    const int cap_i = c.nw * c.rb - 2 * c.T, cap_j = 32 * c.cb - 2 * c.T;
+    if (cap_i < 1 || cap_j < 1) return false;
+    int64_t PI = (nx + cap_i - 1) / cap_i, PJ = (ny + cap_j - 1) / cap_j;
+    if (PI * PJ > sms) return false;
+    // halos come from the adjacent tiles only, and a thread's block never touches two opposite tile edges
+    if (PI > 1 && nx / PI < 2 * c.T + c.rb - 1) return false;
+    if (PJ > 1 && ny / PJ < 2 * c.T + c.cb - 1) return false;
+    c.PI = (int)PI; c.PJ = (int)PJ;
+    return true;
+}
+
+int f2_max_warps(int rb, int cb) { return rb * cb > 8 ? 12 : (rb * cb > 4 ? 16 : 20); }   // register budgets
+
+bool pick_f2_config(int64_t tmax, int64_t nx, int64_t ny, F2Config &best) {
+    const int sms = npb::st().sm_count;
+    if (const char *e = getenv("NPB_F2R_CFG")) {          // "rb,cb,nw,T": experiments
+        F2Config c{0, 0, 0, 0, 0, 0};
+        if (sscanf(e, "%d,%d,%d,%d", &c.rb, &c.cb, &c.nw, &c.T) == 4 && (c.rb == 2 || c.rb == 4 || c.rb == 8) && c.cb == 2 &&
+            c.nw >= 1 && c.nw <= f2_max_warps(c.rb, c.cb) && c.T >= 1 && f2_tiles(nx, ny, sms, c)) { best = c; return true; }
+        return false;
+    }
+    static const int shapes[][2] = {{2, 2}, {4, 2}, {8, 2}};
+    double best_cost = -1.0;
+    for (const auto &sh : shapes)
+        for (int nw = 1; nw <= f2_max_warps(sh[0], sh[1]); ++nw)
+            for (int T = 1; T <= 16 && T <= tmax; ++T) {
+                F2Config c{sh[0], sh[1], nw, T, 0, 0};
+                if (!f2_tiles(nx, ny, sms, c)) continue;
+                const double cost = f2_cost(c);
+                if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; best = c; }
+            }
+    return best_cost >= 0.0 && best_cost <= 2.5;          // beyond that one launch per step is as fast
+}
+
+template <int RB, int CB, int MAXT>
+int f2_launch(const f2rt::Params &rp, size_t smem) {
+    static size_t cfg[NPB_MAX_DEVICES] = {0};                         // per device
+    size_t &configured = cfg[npb::cur_device()];
+    auto kern = f2rt::fdtd2d_regtile_kernel<RB, CB, MAXT>;
+    if (smem > configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError(); return 0;
+        }
+        configured = smem;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, rp.NW * 32, smem) != cudaSuccess) {
+        cudaGetLastError(); return 0;
+    }
+    if ((long)per_sm * npb::st().sm_count < (long)rp.PI * rp.PJ) return 0;       // all CTAs must be co-resident
+    f2rt::Params q = rp;
+    void *args[] = {&q};
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)kern, dim3(rp.PI * rp.PJ), dim3(rp.NW * 32), args, smem,
+                                                npb::st().stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 1;
+}
+
+// Returns 1 if the resident kernel ran, 0 if the grid is not eligible, < 0 on a launch error.
+int try_f2_regtile(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz, const double *fict) {
+    if (tmax < 1 || nx < 1 || ny < 1 || nx * ny > (1LL << 22)) return 0;
+    F2Config c;
+    if (!pick_f2_config(tmax, nx, ny, c)) return 0;
+    const size_t cells = (size_t)c.nw * c.rb * 32 * c.cb;
+    const size_t smem = (size_t)6 * (c.nw + 2) * 32 * c.cb * sizeof(double) + (size_t)c.nw * 32 * sizeof(f2rt::Desc);
+    if (smem + 2048 > npb::st().smem_optin) return 0;
+    const size_t words = (size_t)c.PI * c.PJ * f2rt::SLOTS * 3 * cells;
+    if (words >= (1ULL << 31)) return 0;
+    unsigned long long *inbox = nullptr;
+    if (c.PI * c.PJ > 1) {
+        inbox = (unsigned long long *)npb::workspace(4, words * sizeof(unsigned long long));
+        if (!inbox) return 0;
+        const int geo[8] = {c.rb * 16 + c.cb, c.nw, c.T, c.PI, c.PJ, (int)nx, (int)ny, 0};
+        if (g_f2_armed.box != inbox || g_f2_armed.words != words || memcmp(g_f2_armed.geo, geo, sizeof(geo)) != 0) {
+            // first call on this geometry (or the workspace moved): arm every inbox cell; a completed run leaves them armed
+            f2rt::fdtd2d_inbox_arm_kernel<<<4 * npb::st().sm_count, 256, 0, npb::st().stream>>>(inbox, words);
+            if (cudaGetLastError() != cudaSuccess) return -1;
+            npb::count_launch();
+            g_f2_armed.box = inbox; g_f2_armed.words = words; memcpy(g_f2_armed.geo, geo, sizeof(geo));
+        }
+    }
+    f2rt::Params rp{(int)nx, (int)ny, c.PI, c.PJ, c.T, (int)tmax, c.nw, ex, ey, hz, fict, inbox};
+    int r = 0;
+    if (c.rb == 2) r = f2_launch<2, 2, 640>(rp, smem);
+    else if (c.rb == 4) r = f2_launch<4, 2, 512>(rp, smem);
+    else r = f2_launch<8, 2, 384>(rp, smem);
+    if (r == 1) { npb::count_launch(); g_f2_last = c; }
+    else g_f2_armed.box = nullptr;
+    return r;
+}
 
 }  // namespace
 
-// mode & 3: 0 = dispatch by size (marching passes of up to four steps for grids of >= 4M cells,
-// else one launch per step), 1 = always one launch per step, 2 = marching passes at any size;
+// mode & 3: 0 = dispatch by size (grids that fit on chip -- NPBench S / M / L -- run in ONE cooperative launch,
+// fdtd2d_regtile_kernel; marching passes of up to five steps for grids of >= 4M cells, else one launch per step),
+// 1 = always one launch per step, 2 = marching passes at any size, 3 = same as 0;
 // mode >> 8: rows per chunk of the marching kernel (0 = automatic)
 extern "C" int npb_fdtd2d_set_mode(int mode) {
     g_fd_mode = mode & 3;
@@ -108,6 +224,14 @@ extern "C" int npb_fdtd2d_set_mode(int mode) {
     return 0;
 }
 extern "C" int npb_fdtd2d_last_path(void) { return g_fd_last; }
+// configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, steps per
+// halo exchange, tiles along i, tiles along j}
+extern "C" int npb_fdtd2d_regtile_config(int *out6) {
+    if (!out6) return npb::fail("npb_fdtd2d_regtile_config", "null output");
+    out6[0] = g_f2_last.rb; out6[1] = g_f2_last.cb; out6[2] = g_f2_last.nw; out6[3] = g_f2_last.T;
+    out6[4] = g_f2_last.PI; out6[5] = g_f2_last.PJ;
+    return 0;
+}
 
 // host logic only (no device work): the pass plan npb_fdtd2d_f64 uses; writes min(passes, cap) entries
 extern "C" int npb_fdtd2d_pass_plan(int64_t tmax, int march, int32_t *steps, int cap) {
@@ -149,6 +273,12 @@ extern "C" int npb_fdtd2d_f64(int64_t tmax, int64_t nx, int64_t ny, double *ex, 
     NPB_REQUIRE_INIT();
     NPB_ARG(nx >= 0 && ny >= 0, "npb_fdtd2d_f64", "negative extent");
     if (tmax <= 0 || nx == 0 || ny == 0) return 0;
+    if (g_fd_mode == 0 || g_fd_mode == 3) {   // grids that fit on chip: all three fields in registers for the whole time loop
+        const int r = try_f2_regtile(tmax, nx, ny, ex, ey, hz, fict);
+        if (r < 0) return npb::fail("npb_fdtd2d_f64", "cooperative launch of fdtd2d_regtile_kernel failed (is the GPU "
+                                                      "shared with other work?); no silent fallback to the slow path");
+        if (r == 1) { g_fd_last = 3; return 0; }
+    }
     const size_t cells = (size_t)nx * (size_t)ny;
     double *ws = (double *)npb::workspace(0, 3 * cells * sizeof(double));
     NPB_ARG(ws != nullptr, "npb_fdtd2d_f64", "cannot allocate the ping-pong workspace");
