@@ -34,6 +34,10 @@ void *workspace(int slot, size_t bytes);
 
 inline void count_launch(int n = 1) { st().launches += (uint64_t)n; }
 
+// jacobi2d.cu: host-buffer call of a grid in the marching regime, pipelined over row chunks (H2D of chunk c + 1, the
+// passes skewed by one chunk each, D2H of finished chunks all overlap).  1 = done, 0 = not eligible, < 0 error.
+int jacobi2d_host_pipelined(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B);
+
 // ---- CUDA-graph cache for launch-bound time loops (runtime.cu) --------------------
 // A time loop of hundreds of tiny dependent launches is bound by launch cost.  The entry
 // points capture their launch sequence once per (kernel family, extents, step count,

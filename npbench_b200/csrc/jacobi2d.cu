@@ -19,6 +19,8 @@
 // (oracle/stencil_oracle.c: jacobi2d_sweep); compiled with -fmad=false.
 #include <cooperative_groups.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "inbox.cuh"
 
@@ -381,6 +383,150 @@ extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const 
         return launch_jm(nsteps, ni, nj, src, dst, g_jacobi_rc, row_lo, row_hi);
     }
     return launch_block(0, nsteps, ni, nj, src, dst, tile_row_lo, tile_row_hi);   // the sharded driver's big tile
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-buffer call of an HBM-sized grid (what bench.py's e2e times): 13 GB of A and B cross PCIe in each direction
+// and take 15 times longer than the sweeps, so the call is a pipeline over row chunks:
+//   * B's interior is dead on entry (the first sweep overwrites all of it): only A and B's border ring go up;
+//   * pass p (the marching passes of npb_jacobi2d_f64, same plan) runs on chunk c as soon as pass p - 1 has done
+//     chunks c - 1 .. c + 1 -- one compute stream, passes skewed by one chunk per step, ascending within a step;
+//   * chunk c + 1 of A is uploaded (copy-in stream) while chunk c is computed, and chunk c of B / of A goes back
+//     (copy-out stream) as soon as the last pass that writes it has run there.
+// Results are those of npb_jacobi2d_f64 bit for bit (same kernels on row ranges, as in the sharded driver).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void jacobi2d_border_cols_kernel(double *B, const double *cols, long long ni, long long nj) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= ni) return;
+    B[r * nj] = cols[2 * r];
+    B[r * nj + nj - 1] = cols[2 * r + 1];
+}
+
+struct PipeStreams { cudaStream_t in = nullptr, out = nullptr; double *stage = nullptr; size_t stage_n = 0; };
+PipeStreams g_pipe[NPB_MAX_DEVICES];
+
+// the pass plan of npb_jacobi2d_f64 (marching): n odd passes of odd length covering 2 (TSTEPS - 1) - 1 sweeps, then one sweep
+int jacobi_pass_plan(int64_t tsteps, int64_t max_block, int *ns, int cap) {
+    const int64_t M = 2 * (tsteps - 1) - 1;
+    int64_t n = (M + max_block - 1) / max_block;
+    if ((n & 1) == 0) ++n;
+    int64_t extra_pairs = (M - n) / 2;
+    const int64_t lim = (max_block - 1) / 2;
+    if (n + 1 > cap) return -1;
+    for (int64_t p = 0; p < n; ++p) {
+        const int64_t left = n - p;
+        int64_t take = (extra_pairs + left - 1) / left;
+        if (take > lim) take = lim;
+        extra_pairs -= take;
+        ns[p] = (int)(1 + 2 * take);
+    }
+    ns[n] = 1;
+    return (int)(n + 1);
+}
+
+}  // namespace
+
+int npb::jacobi2d_host_pipelined(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {
+    // experiments / tests (read at every call): smallest grid that is pipelined, rows per chunk
+    const long long min_cells = getenv("NPB_J2_PIPE_MIN_CELLS") ? atoll(getenv("NPB_J2_PIPE_MIN_CELLS")) : JM_AUTO_MIN_CELLS;
+    const long long rows_env = getenv("NPB_J2_PIPE_ROWS") ? atoll(getenv("NPB_J2_PIPE_ROWS")) : 0;
+    if (!(g_jacobi_mode == 0 || g_jacobi_mode == 3) || tsteps < 3 || nj < 8 || ni < 3) return 0;
+    if (ni * nj < min_cells || (g_jacobi_mode == 0 && nj < 4 * JM_STRIP)) return 0;
+    const long long R = rows_env > 0 ? (rows_env < 16 ? 16 : rows_env) : 256;       // rows per chunk (>= sweeps per pass)
+    const long long C = (ni + R - 1) / R;
+    if (C < 4) return 0;
+    static const int march_max = getenv("NPB_J2_MAXNS") ? atoi(getenv("NPB_J2_MAXNS")) : 7;
+    int ns[512];
+    const int P = jacobi_pass_plan(tsteps, march_max >= 7 ? 7 : march_max >= 5 ? 5 : 3, ns, 512);
+    if (P < 2) return 0;
+    const size_t bytes = (size_t)ni * (size_t)nj * sizeof(double);
+    auto err = [](const char *w, cudaError_t e) { return -npb::fail_cuda(w, e); };
+#define PIPE_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { rc = err(#call, e_); goto done; } } while (0)
+    PipeStreams &ps = g_pipe[npb::cur_slot()];
+    int rc = 1;
+    void *pA = nullptr, *pB = nullptr;
+    std::vector<cudaEvent_t> ev;
+    cudaStream_t sc = npb::st().stream;
+    double *dA, *dB, *dcols;
+    if (!ps.in) {
+        if (cudaStreamCreateWithFlags(&ps.in, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ps.out, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ps.in = ps.out = nullptr; return 0; }
+    }
+    if (ps.stage_n < (size_t)(2 * ni)) {
+        if (ps.stage) cudaFreeHost(ps.stage);
+        ps.stage = nullptr; ps.stage_n = 0;
+        if (cudaHostAlloc((void **)&ps.stage, (size_t)(2 * ni) * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return 0; }
+        ps.stage_n = (size_t)(2 * ni);
+    }
+    dcols = (double *)npb::workspace(8, (size_t)(2 * ni) * sizeof(double));
+    if (!dcols) return 0;
+    if (npb_malloc(bytes, &pA) || npb_malloc(bytes, &pB)) { if (pA) npb_free(pA); return -1; }
+    dA = (double *)pA; dB = (double *)pB;
+    ev.resize((size_t)(3 * C + 2), nullptr);
+    for (auto &e : ev) PIPE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        cudaEvent_t *in_done = ev.data(), *b_done = ev.data() + C, *a_done = ev.data() + 2 * C;
+        cudaEvent_t ev_entry = ev[3 * C], ev_border = ev[3 * C + 1];
+        // the copy streams start after whatever the compute stream still does with these (pooled) buffers
+        PIPE_CUDA(cudaEventRecord(ev_entry, sc));
+        PIPE_CUDA(cudaStreamWaitEvent(ps.in, ev_entry, 0));
+        PIPE_CUDA(cudaStreamWaitEvent(ps.out, ev_entry, 0));
+        // B: border ring only (rows 0 and ni - 1, columns 0 and nj - 1 through a pinned staging array)
+        for (int64_t r = 0; r < ni; ++r) { ps.stage[2 * r] = B[r * nj]; ps.stage[2 * r + 1] = B[r * nj + nj - 1]; }
+        PIPE_CUDA(cudaMemcpyAsync(dcols, ps.stage, (size_t)(2 * ni) * sizeof(double), cudaMemcpyHostToDevice, ps.in));
+        PIPE_CUDA(cudaMemcpyAsync(dB, B, (size_t)nj * sizeof(double), cudaMemcpyHostToDevice, ps.in));
+        PIPE_CUDA(cudaMemcpyAsync(dB + (ni - 1) * nj, B + (ni - 1) * nj, (size_t)nj * sizeof(double), cudaMemcpyHostToDevice, ps.in));
+        jacobi2d_border_cols_kernel<<<(unsigned)((ni + 255) / 256), 256, 0, ps.in>>>(dB, dcols, ni, nj);
+        PIPE_CUDA(cudaGetLastError());
+        npb::count_launch();
+        PIPE_CUDA(cudaEventRecord(ev_border, ps.in));
+        PIPE_CUDA(cudaStreamWaitEvent(sc, ev_border, 0));
+        auto rows_of = [&](int64_t c, int64_t &r0, int64_t &r1) { r0 = c * R; r1 = (c + 1) * R < ni ? (c + 1) * R : ni; };
+        int64_t uploaded = 0;
+        auto upload_to = [&](int64_t c_hi) -> cudaError_t {          // chunks [uploaded, c_hi] of A
+            for (; uploaded <= c_hi && uploaded < C; ++uploaded) {
+                int64_t r0, r1; rows_of(uploaded, r0, r1);
+                cudaError_t e = cudaMemcpyAsync(dA + r0 * nj, A + r0 * nj, (size_t)(r1 - r0) * nj * sizeof(double), cudaMemcpyHostToDevice, ps.in);
+                if (e == cudaSuccess) e = cudaEventRecord(in_done[uploaded], ps.in);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        };
+        for (int64_t t = 0; t < C + P - 1; ++t) {
+            PIPE_CUDA(upload_to(t + 2));                              // stay two chunks ahead of pass 0
+            for (int p = 0; p < P; ++p) {
+                const int64_t c = t - p;
+                if (c < 0 || c >= C) continue;
+                if (p == 0) PIPE_CUDA(cudaStreamWaitEvent(sc, in_done[c + 1 < C ? c + 1 : C - 1], 0));
+                int64_t r0, r1; rows_of(c, r0, r1);
+                const int64_t lo = r0 < 1 ? 1 : r0, hi = r1 > ni - 1 ? ni - 1 : r1;
+                if (lo < hi) {
+                    const int e = (p & 1) ? launch_jm(ns[p], ni, nj, dB, dA, g_jacobi_rc, lo, hi) : launch_jm(ns[p], ni, nj, dA, dB, g_jacobi_rc, lo, hi);
+                    if (e) { rc = -e; goto done; }
+                }
+                if (p == P - 2) {                                     // B holds state S - 1 on these rows from now on
+                    PIPE_CUDA(cudaEventRecord(b_done[c], sc));
+                    PIPE_CUDA(cudaStreamWaitEvent(ps.out, b_done[c], 0));
+                    PIPE_CUDA(cudaMemcpyAsync(B + r0 * nj, dB + r0 * nj, (size_t)(r1 - r0) * nj * sizeof(double), cudaMemcpyDeviceToHost, ps.out));
+                }
+                if (p == P - 1) {                                     // A holds state S
+                    PIPE_CUDA(cudaEventRecord(a_done[c], sc));
+                    PIPE_CUDA(cudaStreamWaitEvent(ps.out, a_done[c], 0));
+                    PIPE_CUDA(cudaMemcpyAsync(A + r0 * nj, dA + r0 * nj, (size_t)(r1 - r0) * nj * sizeof(double), cudaMemcpyDeviceToHost, ps.out));
+                }
+            }
+        }
+        g_jacobi_last = 3;
+    }
+done:
+    cudaStreamSynchronize(ps.in); cudaStreamSynchronize(sc); cudaStreamSynchronize(ps.out);
+    for (auto &e : ev) if (e) cudaEventDestroy(e);
+    npb_free(pA); npb_free(pB);
+    if (rc == 1) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) rc = err("jacobi2d host pipeline", e); }
+#undef PIPE_CUDA
+    return rc;
 }
 
 extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {

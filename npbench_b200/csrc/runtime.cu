@@ -53,7 +53,7 @@ static size_t round_size(size_t b) {
 }
 
 struct Workspace { void *p = nullptr; size_t bytes = 0; };
-static Workspace g_ws_all[NPB_MAX_DEVICES][8];
+static Workspace g_ws_all[NPB_MAX_DEVICES][12];
 #define g_ws (g_ws_all[g_cur])
 
 void *workspace(int slot, size_t bytes) {
