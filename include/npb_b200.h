@@ -120,6 +120,9 @@ int npb_jacobi2d_last_path(void);        /* 1 register-tile resident kernel, 2 b
 /* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, sweeps per
  * halo exchange, tiles along i, tiles along j, CTAs per SM} */
 int npb_jacobi2d_regtile_config(int *out7);
+/* host logic only (no device work): the configuration a grid would run with on `sms` SMs; 1 and out7 filled, or 0
+ * if the grid does not run resident */
+int npb_jacobi2d_regtile_plan(int64_t tsteps, int64_t ni, int64_t nj, int sms, int *out7);
 int npb_jacobi2d_tile_rows(void);        /* rows per tile of the blocked kernel */
 
 /* kernel(TSTEPS, A, B): polybench/heat_3d/heat_3d_numpy.py:4-20.  (n0,n1,n2). */
@@ -159,6 +162,7 @@ int npb_fdtd2d_last_path(void);          /* last call: 1 one launch per step, 2 
 /* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, steps per
  * halo exchange, tiles along i, tiles along j} */
 int npb_fdtd2d_regtile_config(int *out6);
+int npb_fdtd2d_regtile_plan(int64_t tmax, int64_t nx, int64_t ny, int sms, int *out6);   /* host logic only, as above */
 /* host logic only: the steps-per-pass plan of npb_fdtd2d_f64 (march != 0: up to five steps per pass, an even
  * number of passes when TMAX allows); writes min(passes, cap) entries, returns the number of passes */
 int npb_fdtd2d_pass_plan(int64_t tmax, int march, int32_t *steps, int cap);

@@ -134,8 +134,7 @@ bool f2_tiles(int64_t nx, int64_t ny, int sms, F2Config &c) {
 
 int f2_max_warps(int rb, int cb) { return rb * cb > 8 ? 12 : (rb * cb > 4 ? 16 : 20); }   // register budgets
 
-bool pick_f2_config(int64_t tmax, int64_t nx, int64_t ny, F2Config &best) {
-    const int sms = npb::st().sm_count;
+bool pick_f2_config(int64_t tmax, int64_t nx, int64_t ny, int sms, F2Config &best) {
     if (const char *e = getenv("NPB_F2R_CFG")) {          // "rb,cb,nw,T": experiments
         F2Config c{0, 0, 0, 0, 0, 0};
         if (sscanf(e, "%d,%d,%d,%d", &c.rb, &c.cb, &c.nw, &c.T) == 4 && (c.rb == 2 || c.rb == 4 || c.rb == 8) && c.cb == 2 &&
@@ -183,7 +182,7 @@ int f2_launch(const f2rt::Params &rp, size_t smem) {
 int try_f2_regtile(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey, double *hz, const double *fict) {
     if (tmax < 1 || nx < 1 || ny < 1 || nx * ny > (1LL << 22)) return 0;
     F2Config c;
-    if (!pick_f2_config(tmax, nx, ny, c)) return 0;
+    if (!pick_f2_config(tmax, nx, ny, npb::st().sm_count, c)) return 0;
     const size_t cells = (size_t)c.nw * c.rb * 32 * c.cb;
     const size_t smem = (size_t)6 * (c.nw + 2) * 32 * c.cb * sizeof(double) + (size_t)c.nw * 32 * sizeof(f2rt::Desc);
     if (smem + 2048 > npb::st().smem_optin) return 0;
@@ -224,6 +223,14 @@ extern "C" int npb_fdtd2d_set_mode(int mode) {
     return 0;
 }
 extern "C" int npb_fdtd2d_last_path(void) { return g_fd_last; }
+// host logic only: the configuration the register-tile kernel would run a grid with on `sms` SMs (1, out6 filled) or 0
+extern "C" int npb_fdtd2d_regtile_plan(int64_t tmax, int64_t nx, int64_t ny, int sms, int *out6) {
+    F2Config c{0, 0, 0, 0, 0, 0};
+    if (!out6 || tmax < 1 || nx < 1 || ny < 1 || nx * ny > (1LL << 22) || sms < 1) return 0;
+    if (!pick_f2_config(tmax, nx, ny, sms, c)) return 0;
+    out6[0] = c.rb; out6[1] = c.cb; out6[2] = c.nw; out6[3] = c.T; out6[4] = c.PI; out6[5] = c.PJ;
+    return 1;
+}
 // configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, steps per
 // halo exchange, tiles along i, tiles along j}
 extern "C" int npb_fdtd2d_regtile_config(int *out6) {

@@ -192,8 +192,7 @@ int j2_max_warps(int rb, int cb, int per_sm) {
     return (rb * cb > 8 ? 512 : 576) / 32;
 }
 
-bool pick_regtile_config(int64_t nsweeps, int64_t ni, int64_t nj, J2Config &best) {
-    const int sms = npb::st().sm_count;
+bool pick_regtile_config(int64_t nsweeps, int64_t ni, int64_t nj, int sms, J2Config &best) {
     const int64_t in0 = ni - 2, in1 = nj - 2;
     // NPB_J2R_CFG="rb,cb,nw,T[,per_sm]": experiments
     if (const char *e = getenv("NPB_J2R_CFG")) {
@@ -250,7 +249,7 @@ int j2_launch(const j2rt::Params &rp, size_t smem) {
 int try_regtile(int64_t nsweeps, int64_t ni, int64_t nj, double *A, double *B) {
     if (nsweeps < 2 || (nsweeps & 1) || ni < 3 || nj < 3 || ni * nj > (1LL << 22)) return 0;
     J2Config c;
-    if (!pick_regtile_config(nsweeps, ni, nj, c)) return 0;
+    if (!pick_regtile_config(nsweeps, ni, nj, npb::st().sm_count, c)) return 0;
     const size_t cells = (size_t)c.nw * c.rb * 32 * c.cb;
     const size_t smem = (2 * cells + (size_t)4 * (c.nw + 2) * 32 * c.cb) * sizeof(double) + (size_t)c.nw * 32 * sizeof(j2rt::Desc);
     if ((smem + 1024) * c.per_sm + 1024 > npb::st().smem_optin) return 0;
@@ -363,6 +362,16 @@ extern "C" int npb_jacobi2d_regtile_config(int *out7) {
 }
 
 extern "C" int npb_jacobi2d_tile_rows(void) { return TileBig::TI; }
+
+// host logic only (no device work): the configuration the register-tile kernel would run a grid with on `sms` SMs;
+// returns 1 and fills out7 (layout of npb_jacobi2d_regtile_config), or 0 if the grid does not run resident
+extern "C" int npb_jacobi2d_regtile_plan(int64_t tsteps, int64_t ni, int64_t nj, int sms, int *out7) {
+    J2Config c{0, 0, 0, 0, 0, 0, 1};
+    if (!out7 || tsteps < 2 || ni < 3 || nj < 3 || ni * nj > (1LL << 22) || sms < 1) return 0;
+    if (!pick_regtile_config(2 * (tsteps - 1), ni, nj, sms, c)) return 0;
+    out7[0] = c.rb; out7[1] = c.cb; out7[2] = c.nw; out7[3] = c.T; out7[4] = c.PI; out7[5] = c.PJ; out7[6] = c.per_sm;
+    return 1;
+}
 
 extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src,
                                       double *dst, int64_t tile_row_lo, int64_t tile_row_hi) {
