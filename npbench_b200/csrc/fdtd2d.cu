@@ -132,7 +132,7 @@ bool f2_tiles(int64_t nx, int64_t ny, int sms, F2Config &c) {
     return true;
 }
 
-int f2_max_warps(int rb, int cb) { return rb * cb > 8 ? 12 : (rb * cb > 4 ? 16 : 20); }   // register budgets
+int f2_max_warps(int rb, int cb) { return rb * cb > 8 ? 16 : (rb * cb > 4 ? 16 : 20); }   // register budgets
 
 bool pick_f2_config(int64_t tmax, int64_t nx, int64_t ny, int sms, F2Config &best) {
     if (const char *e = getenv("NPB_F2R_CFG")) {          // "rb,cb,nw,T": experiments
@@ -205,7 +205,8 @@ int try_f2_regtile(int64_t tmax, int64_t nx, int64_t ny, double *ex, double *ey,
     int r = 0;
     if (c.rb == 2) r = f2_launch<2, 2, 640>(rp, smem);
     else if (c.rb == 4) r = f2_launch<4, 2, 512>(rp, smem);
-    else r = f2_launch<8, 2, 384>(rp, smem);
+    else if (c.nw <= 12) r = f2_launch<8, 2, 384>(rp, smem);
+    else r = f2_launch<8, 2, 512>(rp, smem);          // 128 registers: ~100 bytes of spills outside the step loop
     if (r == 1) { npb::count_launch(); g_f2_last = c; }
     else g_f2_armed.box = nullptr;
     return r;
