@@ -16,11 +16,13 @@
 //     of a region edge that faces another tile hold garbage after q sweeps of a block -- the tile itself sits T cells
 //     inside and never sees it (the classic redundant-halo scheme, here without any shared-memory tile).  After the
 //     T-th sweep every thread sends the cells of its tile that lie within T of a tile edge straight from its
-//     registers into the (up to 8) neighbours' inboxes, and the threads that hold halo cells poll them straight into
-//     their registers (sentinel protocol of inbox.cuh: relaxed gpu-scope stores / loads on the value itself, re-arm
-//     after consumption, a gpu-scope fence every FENCE_EVERY exchanges, ring of SLOTS exchange slots).  One SM-to-SM
-//     signal through the L2 costs 0.43 us on this machine (tools/pingpong.cu) -- about two sweeps of arithmetic -- so
-//     T trades redundant rim work against exposed round trips; the host picks it per grid (pick_regtile_config).
+//     registers into the inboxes of the neighbour tiles that hold them as halo (a thread's block has at most three:
+//     vertical, horizontal, diagonal), and the threads that hold halo cells poll them straight into their registers
+//     (sentinel protocol of inbox.cuh: relaxed gpu-scope stores / loads on the value itself, re-arm after
+//     consumption, ring of SLOTS exchange slots, a gpu-scope fence before the sends of every FENCE_EVERY-th
+//     exchange).  One exchange costs ~2 us (tools/pingpong.cu: 0.43 us for two CTAs, 1.7 us when 144 exchange at
+//     once) -- several sweeps of arithmetic -- so T trades redundant rim work against exposed round trips; the
+//     host picks it per grid from a cost model (pick_regtile_config in jacobi2d.cu).
 //   * The constant border ring: even states carry A's border, odd states B's (jacobi_2d_numpy.py never writes them).
 //     Region cells on the ring or outside the grid are "fixed": after every sweep their registers are reloaded from a
 //     per-parity shared copy, so neighbours see exactly the border value.  Only threads that own such cells pay.
