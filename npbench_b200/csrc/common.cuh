@@ -82,6 +82,26 @@ int graph_end_and_launch(const GraphKey &key, int rc);
         if (!(cond)) return npb::fail(where, msg);                                \
     } while (0)
 
+// Programmatic dependent launch for chains of short dependent kernels (one launch per sweep / time step, replayed as
+// a CUDA graph): the next kernel of the chain is launched while this one still runs -- its CTAs take their SM slots
+// as soon as these free up and wait in pdl_wait() until this grid has completed and its stores are visible -- so the
+// ~1.5 us of launch latency between two dependent graph nodes overlaps with the predecessor instead of following it.
+// A kernel launched with pdl_launch() MUST call pdl_wait() before its first access to memory a predecessor wrote or
+// read, on every path.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Streaming (read-once) global load / store-once helpers.
 __device__ __forceinline__ double ldg_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(double *p, double v) { __stcs(p, v); }

@@ -34,6 +34,7 @@ struct FdtdParams {
 
 __global__ void __launch_bounds__(FD_THREADS)
 fdtd2d_step_kernel(FdtdParams p) {
+    pdl_wait();                                // launched with pdl_launch (common.cuh)
     const long long j = (long long)blockIdx.y * FD_THREADS + threadIdx.x;
     const long long i = p.r_lo + blockIdx.x;   // local row
     if (j >= p.ny) return;
@@ -74,7 +75,13 @@ int launch_step(const FdtdParams &p) {
     const long long jb = (p.ny + FD_THREADS - 1) / FD_THREADS;
     if (jb > 65535 || rows >= (1LL << 31)) return npb::fail("fdtd2d", "grid too large");
     dim3 grid((unsigned)rows, (unsigned)jb);
-    fdtd2d_step_kernel<<<grid, FD_THREADS, 0, npb::st().stream>>>(p);
+    static const bool pdl = !(getenv("NPB_PDL") && atoi(getenv("NPB_PDL")) == 0);
+    if (pdl) {
+        if (pdl_launch(fdtd2d_step_kernel, grid, dim3(FD_THREADS), 0, npb::st().stream, p) != cudaSuccess)
+            return npb::fail_cuda("fdtd2d_step_kernel", cudaGetLastError());
+    } else {
+        fdtd2d_step_kernel<<<grid, FD_THREADS, 0, npb::st().stream>>>(p);
+    }
     NPB_CHECK_LAUNCH("fdtd2d_step_kernel");
     npb::count_launch();
     return 0;

@@ -21,11 +21,15 @@
 namespace {
 
 constexpr int H3_THREADS = 256;
-constexpr int H3_U = 2;              // planes per unrolled marching step of the streaming kernel
-
+// planes per unrolled marching step of the streaming kernel: all 5 * H3_U loads of a step are issued before the first
+// use.  2 for grids beyond L2 (640^3: HBM bound); 4 for L2-resident grids that run as a single wave of CTAs, where the
+// L2 round trips of a thread's few steps are the whole kernel (120^3 = `paper`: 5.63 -> 5.20 ms; 160^3 and 200^3 are
+// slower with 4)
+template <int H3_U>
 __global__ void __launch_bounds__(H3_THREADS)
 heat3d_sweep_kernel(int n1, int n2, long long plane, const double *__restrict__ src,
                     double *__restrict__ dst, long long i_lo, long long i_hi, int planes_per_chunk) {
+    pdl_wait();                                                             // launched with pdl_launch (common.cuh)
     const long long c = (long long)blockIdx.x * H3_THREADS + threadIdx.x;   // flat (j,k)
     if (c >= plane) return;
     const int j = (int)(c / n2), k = (int)(c % n2);
@@ -356,8 +360,17 @@ int launch_sweep(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
     long long chunks = (planes + ppc - 1) / ppc;
     while (chunks > 65535) { ppc <<= 1; chunks = (planes + ppc - 1) / ppc; }
     dim3 grid((unsigned)col_blocks, (unsigned)chunks);
-    heat3d_sweep_kernel<<<grid, H3_THREADS, 0, npb::st().stream>>>(
-        (int)n1, (int)n2, plane, src, dst, (long long)i_lo, (long long)i_hi, (int)ppc);
+    static const bool pdl = !(getenv("NPB_PDL") && atoi(getenv("NPB_PDL")) == 0);
+    static const long long u4_max = getenv("NPB_HEAT_U4_MAX") ? atoll(getenv("NPB_HEAT_U4_MAX")) : 3000000;
+    const bool u4 = n0 * n1 * n2 <= u4_max;       // tried at 120^3: 8 planes per step 8.4 ms, 4 planes with 4 / 6 / 10 / 12 / 16 planes per chunk 5.7 / 6.0 / 5.35 / 5.4 / 6.1 ms
+    auto kern = u4 ? heat3d_sweep_kernel<4> : heat3d_sweep_kernel<2>;
+    if (pdl) {
+        if (pdl_launch(kern, grid, dim3(H3_THREADS), 0, npb::st().stream, (int)n1, (int)n2, plane, src, dst,
+                       (long long)i_lo, (long long)i_hi, (int)ppc) != cudaSuccess)
+            return npb::fail_cuda("heat3d_sweep_kernel", cudaGetLastError());
+    } else {
+        kern<<<grid, H3_THREADS, 0, npb::st().stream>>>((int)n1, (int)n2, plane, src, dst, (long long)i_lo, (long long)i_hi, (int)ppc);
+    }
     NPB_CHECK_LAUNCH("heat3d_sweep_kernel");
     npb::count_launch();
     return 0;
