@@ -123,7 +123,7 @@ double f2_cost(const F2Config &c) {
     const double mio = 4.0 * c.rb + 12.0 * c.cb, fp64 = (11.0 * cells + 3.0 * c.cb) / 2.0;
     const double per_warp = 1.15 * (mio > fp64 ? mio : fp64) / 1965.0;
     const double step = 0.20 + 0.02 * cells + c.nw * per_warp;
-    const double exchange = (c.PI * c.PJ > 1) ? 2.6 : 0.0;
+    const double exchange = (c.PI * c.PJ > 1) ? 4.5 : 0.0;         // three fields: measured 4 - 6.6 us per exchange
     return step + exchange / c.T;
 }
 
@@ -148,7 +148,9 @@ bool pick_f2_config(int64_t tmax, int64_t nx, int64_t ny, int sms, F2Config &bes
             c.nw >= 1 && c.nw <= f2_max_warps(c.rb, c.cb) && c.T >= 1 && f2_tiles(nx, ny, sms, c)) { best = c; return true; }
         return false;
     }
-    static const int shapes[][2] = {{2, 2}, {4, 2}, {8, 2}};
+    // 2 x 2 cells per thread only when forced: the model likes its many small warps at preset S, the measurement
+    // (profiles/r02_f2rt_full_sweep.log) does not (0.031 vs 0.027 ms)
+    static const int shapes[][2] = {{4, 2}, {8, 2}};
     double best_cost = -1.0;
     for (const auto &sh : shapes)
         for (int nw = 1; nw <= f2_max_warps(sh[0], sh[1]); ++nw)
