@@ -31,6 +31,7 @@ struct CavCoef {
 // build_up_b (:15-23): interior of b
 __global__ void cavity_b_kernel(int nx, int ny, CavCoef k, const double *__restrict__ u, const double *__restrict__ v,
                                 double *__restrict__ b) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = 1 + blockIdx.x * blockDim.x + threadIdx.x, i = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 2 || j > nx - 2) return;
     const double a1 = (CAV_AT(u, i, j + 1) - CAV_AT(u, i, j - 1)) / k.c2dx;
@@ -48,6 +49,7 @@ __global__ void cavity_b_kernel(int nx, int ny, CavCoef k, const double *__restr
 // (0,0) and (0,nx-1) that of (1,1) and (1,nx-2)).
 __global__ void cavity_p_kernel(int nx, int ny, CavCoef k, const double *__restrict__ pn, double *__restrict__ p,
                                 const double *__restrict__ b) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = 1 + blockIdx.x * blockDim.x + threadIdx.x, i = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 2 || j > nx - 2) return;
     const double val = ((((CAV_AT(pn, i, j + 1) + CAV_AT(pn, i, j - 1)) * k.dy2) + ((CAV_AT(pn, i + 1, j) + CAV_AT(pn, i - 1, j)) * k.dx2)) / k.den) -
@@ -71,6 +73,7 @@ __global__ void cavity_p_kernel(int nx, int ny, CavCoef k, const double *__restr
 // momentum update (:56-87): (un, vn, p) -> (u, v), boundary cells included (lid row ny-1: u = 1)
 __global__ void cavity_uv_kernel(int nx, int ny, CavCoef k, const double *__restrict__ un, const double *__restrict__ vn,
                                  const double *__restrict__ p, double *__restrict__ u, double *__restrict__ v) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 1 || j > nx - 1) return;
     if (i == 0 || j == 0 || i == ny - 1 || j == nx - 1) {
@@ -127,12 +130,12 @@ extern "C" int npb_cavity_flow_f64(int64_t nx, int64_t ny, int64_t nt, int64_t n
     cudaStream_t st = npb::st().stream;
     int pc = 0, uc = 0, rc = 0;
     for (int64_t n = 0; n < nt && !rc; ++n) {
-        cavity_b_kernel<<<grid_in, blk, 0, st>>>((int)nx, (int)ny, k, ubuf[uc], vbuf[uc], b);
+        pdl_launch(cavity_b_kernel, grid_in, blk, 0, st, (int)nx, (int)ny, k, (const double *)ubuf[uc], (const double *)vbuf[uc], b);
         for (int64_t q = 0; q < nit; ++q) {
-            cavity_p_kernel<<<grid_in, blk, 0, st>>>((int)nx, (int)ny, k, pbuf[pc], pbuf[pc ^ 1], b);
+            pdl_launch(cavity_p_kernel, grid_in, blk, 0, st, (int)nx, (int)ny, k, (const double *)pbuf[pc], pbuf[pc ^ 1], (const double *)b);
             pc ^= 1;
         }
-        cavity_uv_kernel<<<grid_all, blk, 0, st>>>((int)nx, (int)ny, k, ubuf[uc], vbuf[uc], pbuf[pc], ubuf[uc ^ 1], vbuf[uc ^ 1]);
+        pdl_launch(cavity_uv_kernel, grid_all, blk, 0, st, (int)nx, (int)ny, k, (const double *)ubuf[uc], (const double *)vbuf[uc], (const double *)pbuf[pc], ubuf[uc ^ 1], vbuf[uc ^ 1]);
         uc ^= 1;
         if (cudaGetLastError() != cudaSuccess) rc = npb::fail("npb_cavity_flow_f64", "kernel launch failed");
         npb::count_launch((int)(nit + 2));

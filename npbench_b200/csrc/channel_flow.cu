@@ -31,6 +31,7 @@ struct ChCoef {
 
 __global__ void channel_b_kernel(int nx, int ny, ChCoef k, const double *__restrict__ u, const double *__restrict__ v,
                                  double *__restrict__ b) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 2 || j > nx - 1) return;
     const int je = (j + 1 == nx) ? 0 : j + 1, jw = (j == 0) ? nx - 1 : j - 1;
@@ -46,6 +47,7 @@ __global__ void channel_b_kernel(int nx, int ny, ChCoef k, const double *__restr
 // one pressure iteration: pn -> p for rows 1..ny-2 (all columns, wrapped), then p[-1,:] = p[-2,:], p[0,:] = p[1,:]
 __global__ void channel_p_kernel(int nx, int ny, ChCoef k, const double *__restrict__ pn, double *__restrict__ p,
                                  const double *__restrict__ b) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = 1 + blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 2 || j > nx - 1) return;
     const int je = (j + 1 == nx) ? 0 : j + 1, jw = (j == 0) ? nx - 1 : j - 1;
@@ -58,6 +60,7 @@ __global__ void channel_p_kernel(int nx, int ny, ChCoef k, const double *__restr
 
 __global__ void channel_uv_kernel(int nx, int ny, ChCoef k, const double *__restrict__ un, const double *__restrict__ vn,
                                   const double *__restrict__ p, double *__restrict__ u, double *__restrict__ v) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (i > ny - 1 || j > nx - 1) return;
     if (i == 0 || i == ny - 1) { CH_AT(u, i, j) = 0.0; CH_AT(v, i, j) = 0.0; return; }     // walls (:158-161)
@@ -77,6 +80,7 @@ __global__ void channel_uv_kernel(int nx, int ny, ChCoef k, const double *__rest
 // ---- np.sum: leaf blocks (8 <= n <= 128) and the combination tree ---------------------------------------------
 __global__ void npsum_leaf_kernel(const double *__restrict__ a, const long long *__restrict__ leaf_start,
                                   const int *__restrict__ leaf_n, int nleaf, double *__restrict__ leaf_sum) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= nleaf) return;
     const double *x = a + leaf_start[l];
@@ -103,6 +107,7 @@ __global__ void npsum_leaf_kernel(const double *__restrict__ a, const long long 
 // prog: post-order walk of pairwise_sum's recursion; entry >= 0: push leaf_sum[entry]; -1: pop b, pop a, push a + b
 __global__ void npsum_tree_kernel(const int *__restrict__ prog, int nprog, const double *__restrict__ leaf_sum,
                                   double *__restrict__ out) {
+    pdl_wait();                                   // launched with pdl_launch (common.cuh)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double stack[48];
     int sp = 0;
@@ -167,8 +172,8 @@ extern "C" int npb_channel_flow_f64(int64_t nit, int64_t nx, int64_t ny, double 
     static double *h_sum = nullptr;                          // pinned: the per-step D2H copy is part of a captured graph
     if (!h_sum) NPB_CUDA(cudaHostAlloc((void **)&h_sum, 64, cudaHostAllocDefault));
     auto enqueue_sum = [&](const double *a) -> int {        // np.sum(a) -> *h_sum (valid after a stream sync)
-        npsum_leaf_kernel<<<(unsigned)((nleaf + 127) / 128), 128, 0, st>>>(a, d_ls, d_ln, (int)nleaf, d_leaf);
-        npsum_tree_kernel<<<1, 32, 0, st>>>(d_prog, (int)nprog, d_leaf, d_out);
+        pdl_launch(npsum_leaf_kernel, dim3((unsigned)((nleaf + 127) / 128)), dim3(128), 0, st, a, d_ls, d_ln, (int)nleaf, d_leaf);
+        pdl_launch(npsum_tree_kernel, dim3(1), dim3(32), 0, st, d_prog, (int)nprog, (const double *)d_leaf, d_out);
         npb::count_launch(2);
         return cudaMemcpyAsync(h_sum, d_out, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess;
     };
@@ -196,13 +201,13 @@ extern "C" int npb_channel_flow_f64(int64_t nit, int64_t nx, int64_t ny, double 
         if (!npb::graph_replay(key)) {
             const bool capturing = npb::graph_begin();
             int q_pc = pc_in;
-            channel_b_kernel<<<grid_rows, blk, 0, st>>>((int)nx, (int)ny, k, ubuf[uc_in], vbuf[uc_in], b);
+            pdl_launch(channel_b_kernel, grid_rows, blk, 0, st, (int)nx, (int)ny, k, (const double *)ubuf[uc_in], (const double *)vbuf[uc_in], b);
             for (int64_t q = 0; q < nit; ++q) {
-                channel_p_kernel<<<grid_rows, blk, 0, st>>>((int)nx, (int)ny, k, pbuf[q_pc], pbuf[q_pc ^ 1], b);
+                pdl_launch(channel_p_kernel, grid_rows, blk, 0, st, (int)nx, (int)ny, k, (const double *)pbuf[q_pc], pbuf[q_pc ^ 1], (const double *)b);
                 q_pc ^= 1;
             }
-            channel_uv_kernel<<<grid_all, blk, 0, st>>>((int)nx, (int)ny, k, ubuf[uc_in], vbuf[uc_in], pbuf[q_pc], ubuf[uc_in ^ 1],
-                                                        vbuf[uc_in ^ 1]);
+            pdl_launch(channel_uv_kernel, grid_all, blk, 0, st, (int)nx, (int)ny, k, (const double *)ubuf[uc_in], (const double *)vbuf[uc_in],
+                       (const double *)pbuf[q_pc], ubuf[uc_in ^ 1], vbuf[uc_in ^ 1]);
             npb::count_launch((int)(nit + 2));
             int rc = enqueue_sum(ubuf[uc_in ^ 1]);
             if (cudaGetLastError() != cudaSuccess) rc = 1;

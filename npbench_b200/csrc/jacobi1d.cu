@@ -28,6 +28,7 @@ constexpr int J1_MAX_STEPS = 127;        // sweeps per pass (odd) of the widest 
 template <int J1_C>                     // cells per thread; a warp window has 32 * J1_C cells
 __global__ void __launch_bounds__(32)
 jacobi1d_block_kernel(int nsteps, long long n, const double *__restrict__ src, double *__restrict__ dst) {
+    pdl_wait();                                                       // launched with pdl_launch (common.cuh)
     constexpr int J1_W = 32 * J1_C;
     const int lane = threadIdx.x;
     const long long out = J1_W - 2 * nsteps;                          // cells this warp completes
@@ -77,9 +78,8 @@ int g_cells = 4;      // cells per thread (4, 8 or 16)
 int launch_pass(int nsteps, int64_t n, const double *src, double *dst) {
     const long long out = 32LL * g_cells - 2 * nsteps;
     const long long grid = (n - 2 + out - 1) / out;
-    if (g_cells == 4) jacobi1d_block_kernel<4><<<(unsigned)grid, 32, 0, npb::st().stream>>>(nsteps, n, src, dst);
-    else if (g_cells == 8) jacobi1d_block_kernel<8><<<(unsigned)grid, 32, 0, npb::st().stream>>>(nsteps, n, src, dst);
-    else jacobi1d_block_kernel<16><<<(unsigned)grid, 32, 0, npb::st().stream>>>(nsteps, n, src, dst);
+    auto kern = g_cells == 4 ? jacobi1d_block_kernel<4> : (g_cells == 8 ? jacobi1d_block_kernel<8> : jacobi1d_block_kernel<16>);
+    pdl_launch(kern, dim3((unsigned)grid), dim3(32), 0, npb::st().stream, nsteps, (long long)n, src, dst);
     NPB_CHECK_LAUNCH("jacobi1d_block_kernel");
     npb::count_launch();
     return 0;
