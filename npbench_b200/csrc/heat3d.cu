@@ -400,7 +400,12 @@ int regtile_launch(const regtile::Params &rp, int threads, size_t smem) {
     if ((long)per_sm * npb::st().sm_count < (long)rp.PI * rp.PJ) return 0;      // all CTAs must be co-resident
     regtile::Params q = rp;
     void *args[] = {&q};
-    cudaError_t e = cudaLaunchCooperativeKernel((void *)regtile::heat3d_regtile_kernel<MAXT, TRACE>, dim3(rp.PI * rp.PJ),
+    cudaError_t e;
+    if (g_rt_flags & 16) {
+        regtile::heat3d_regtile_kernel<MAXT, TRACE><<<dim3(rp.PI * rp.PJ), dim3(threads), smem, npb::st().stream>>>(q);
+        e = cudaGetLastError();
+    } else
+    e = cudaLaunchCooperativeKernel((void *)regtile::heat3d_regtile_kernel<MAXT, TRACE>, dim3(rp.PI * rp.PJ),
                                                 dim3(threads), args, smem, npb::st().stream);
     if (e != cudaSuccess) { cudaGetLastError(); return -1; }
     return 1;
@@ -473,7 +478,7 @@ extern "C" int npb_heat3d_set_mode(int mode) {
     g_resident_fences = (mode & 16) ? 0 : 1;
     g_backoff_ns = (mode & 32) ? 50 : ((mode & 64) ? 800 : 200);   // +16: resident kernel without the per-sweep fences (experiments)
     g_mode = mode & 7;
-    g_rt_flags = (mode >> 8) & 7;               // +256 no fences, +512 no polls, +1024 no sends: TIMING EXPERIMENTS, wrong results
+    g_rt_flags = (mode >> 8) & 31;              // +256 no fences, +512 no polls, +1024 no sends: TIMING EXPERIMENTS, wrong results; +4096: plain instead of cooperative launch (no difference measured)
     g_rt_armed.box = nullptr;                   // experiments leave unconsumed cells behind: re-arm
     g_use_graphs = !(mode & 8);                 // +8: plain launches instead of a captured graph
     return 0;
