@@ -194,9 +194,12 @@ int launch_march(int ns, int64_t nx, int64_t ny, const double *ex, const double 
     const long long nstrips = (ny + out_cols - 1) / out_cols;
     const long long blocks_x = (nstrips + FM_WARPS - 1) / FM_WARPS;
     // enough row chunks for ~48 warps per SM over the whole launch; each chunk re-runs 2*ns rows
-    long long chunks = (48LL * npb::st().sm_count + nstrips - 1) / nstrips;
+    static const int rule = getenv("NPB_FDTD_CHUNKS") ? atoi(getenv("NPB_FDTD_CHUNKS")) : 48;
+    static const int env_rc = getenv("NPB_FDTD_RC") ? atoi(getenv("NPB_FDTD_RC")) : 0;
+    long long chunks = ((long long)rule * npb::st().sm_count + nstrips - 1) / nstrips;
     long long rc = (span + chunks - 1) / chunks;
     if (rc < 64) rc = 64;
+    if (env_rc > 0) rc = env_rc;
     if (rc_override > 0) rc = rc_override;
     if (rc > span) rc = span;
     chunks = (span + rc - 1) / rc;

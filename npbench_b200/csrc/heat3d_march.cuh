@@ -222,6 +222,8 @@ int launch_march(int64_t n0, int64_t n1, int64_t n2, const double *src, double *
         const double cost = (double)waves * (double)(planes + 6);
         if (nc == 1 || cost < best_cost * 0.98) { best_nc = nc; best_cost = cost; }
     }
+    static const int env_chunk = getenv("NPB_HEAT_CHUNK") ? atoi(getenv("NPB_HEAT_CHUNK")) : 0;     // planes per chunk
+    if (env_chunk > 0) best_nc = (span + env_chunk - 1) / env_chunk;
     const long chunk = (span + best_nc - 1) / best_nc;
     const long nchunks = (span + chunk - 1) / chunk;
     HmParams p{(int)n0, (int)n1, (int)n2, (int)tiles_k, (int)chunk, (int)i_lo, (int)i_hi, src, dst};
