@@ -42,6 +42,7 @@ struct JmParams {
     int pfd;                   // L2 prefetch distance in rows (0 = off)
     const double *src;
     double *dst;
+    double *dst2;              // DUAL instantiations: the state before the last sweep of the pass goes here (interior only)
 };
 
 template <bool VEC>
@@ -140,7 +141,10 @@ __device__ __forceinline__ void jm_sweeps_pair(double (&P)[NS][2][JM_COLS], doub
     jm_sweep_fast<NS, 1>(P, c1, NS - 1);
 }
 
-template <int NS, bool VEC>
+// DUAL: the pass also stores state NS - 1 (into p.dst2): the closing pass of kernel(TSTEPS, A, B) leaves state S in A and
+// state S - 1 in B (jacobi_2d_numpy.py:8-10) without a separate single-sweep pass over memory.  After the last sweep of
+// a row step P[NS - 1][u] holds the row that entered it -- row r - NS + 1 of state NS - 1 -- so nothing extra is kept.
+template <int NS, bool VEC, bool DUAL>
 __global__ void __launch_bounds__(JM_WARPS * 32, (NS <= 5) ? 3 : 2)
 jacobi2d_march_kernel(JmParams p) {
     static_assert(NS & 1, "a pass must go src -> dst");
@@ -211,6 +215,20 @@ jacobi2d_march_kernel(JmParams p) {
     // wait for the newest load): row r lives in slot (r - r_first) % JM_PF
     static_assert(JM_PF == 2, "the row loop below is written out for two rows in flight");
     JmEdge edge{p.src, p.dst, ni, nj, col0, ring, bw, bm, edge_strip, {inside[0], inside[1], inside[2], inside[3]}};
+    // DUAL: row q2 of state NS - 1 -> dst2 (dst_off points at row q2 - 1)
+    auto store_row2 = [&](const double (&c)[JM_COLS], const long long q2) {
+        if (any_wr && q2 >= r0 && q2 < r1 && q2 >= 1 && q2 <= ni - 2) {
+            double *g = p.dst2 + dst_off + nj;
+            if (vec_wr) {
+                reinterpret_cast<double2 *>(g)[0] = make_double2(c[0], c[1]);
+                reinterpret_cast<double2 *>(g)[1] = make_double2(c[2], c[3]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < JM_COLS; ++m)
+                    if (wr[m]) g[m] = c[m];
+            }
+        }
+    };
     auto row_step = [&](const long long r, auto uc) {
         constexpr int u = decltype(uc)::value;
         double c[JM_COLS];
@@ -247,6 +265,7 @@ jacobi2d_march_kernel(JmParams p) {
                     if (wr[m]) g[m] = c[m];
             }
         }
+        if (DUAL) store_row2(P[NS - 1][u], q_out + 1);
         dst_off += nj;
     };
     auto store_row = [&](const double (&c)[JM_COLS], const long long q_out) {
@@ -281,7 +300,9 @@ jacobi2d_march_kernel(JmParams p) {
             jm_load_row<VEC>(p.src + src_off, nj, col0, full, nxt[1]);
         }
         jm_sweeps_pair<NS>(P, c0, c1);
+        if (DUAL) store_row2(P[NS - 1][0], r - NS + 1);
         store_row(c0, r - NS);
+        if (DUAL) store_row2(P[NS - 1][1], r - NS + 2);
         store_row(c1, r + 1 - NS);
     };
     for (long long rb = r_first; rb <= r_last; rb += JM_PF) {
@@ -296,16 +317,21 @@ jacobi2d_march_kernel(JmParams p) {
 
 template <int NS>
 int launch_jm_ns(const JmParams &p, dim3 grid, bool vec) {
-    if (vec) jacobi2d_march_kernel<NS, true><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
-    else jacobi2d_march_kernel<NS, false><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
+    if (p.dst2) {
+        if (vec) jacobi2d_march_kernel<NS, true, true><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
+        else jacobi2d_march_kernel<NS, false, true><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
+    } else {
+        if (vec) jacobi2d_march_kernel<NS, true, false><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
+        else jacobi2d_march_kernel<NS, false, false><<<grid, JM_WARPS * 32, 0, npb::st().stream>>>(p);
+    }
     NPB_CHECK_LAUNCH("jacobi2d_march_kernel");
     npb::count_launch();
     return 0;
 }
 
-// one pass: ns (1, 3, 5 or 7) sweeps src -> dst
+// one pass: ns (1, 3, 5 or 7) sweeps src -> dst; dst2 != nullptr: the state before the last sweep goes there as well
 int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, int rc_override, int64_t row_lo = 0,
-              int64_t row_hi = -1) {
+              int64_t row_hi = -1, double *dst2 = nullptr) {
     if (row_hi < 0 || row_hi > ni) row_hi = ni;
     if (row_lo < 0) row_lo = 0;
     if (row_lo >= row_hi) return 0;
@@ -313,7 +339,7 @@ int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, in
     const long long out_cols = jm_out_cols(ns);
     const long long nstrips = (nj + out_cols - 1) / out_cols;
     const long long blocks_x = (nstrips + JM_WARPS - 1) / JM_WARPS;
-    const bool vec = (nj % 2 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0);
+    const bool vec = (nj % 2 == 0) && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)dst2) % 16 == 0);
     // Rows per chunk.  Short chunks win by a wide margin although every chunk re-runs 2 * ns ramp rows: the warps of
     // neighbouring strips start a chunk on the same rows and drift apart as they march, and with them the DRAM pages
     // and the shared halo columns they touch.  Measured (ns = 5 / 7, B200): the 10240 x 81920 slab 33.1 ms per 40 sweeps
@@ -333,7 +359,7 @@ int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, in
     const long long chunks = (rows + rc - 1) / rc;
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("jacobi2d", "grid too large");
     static const int pfd = getenv("NPB_J2_PFD") ? atoi(getenv("NPB_J2_PFD")) : 3;
-    JmParams p{ni, nj, nstrips, row_lo, row_hi, (int)rc, pfd, src, dst};
+    JmParams p{ni, nj, nstrips, row_lo, row_hi, (int)rc, pfd, src, dst, dst2};
     dim3 grid((unsigned)blocks_x, (unsigned)chunks);
     switch (ns) {
         case 1: return launch_jm_ns<1>(p, grid, vec);     // the closing single sweep of a big grid: a plain HBM stream
