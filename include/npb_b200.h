@@ -110,6 +110,14 @@ int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *
 #define NPB_JACOBI2D_MAX_BLOCK 7
 int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst,
                            int64_t tile_row_lo, int64_t tile_row_hi);
+/* The same pass, which ALSO stores the state before its last sweep into dst2 (a third array; interior cells of the
+ * same rows).  The closing pass of a sharded run leaves state S in A and state S - 1 in B this way -- no separate
+ * single sweep (no reference counterpart: the reference is single device, jacobi_2d_numpy.py:8-10 define the two
+ * states).  Marching regime only: npb_jacobi2d_block_marches(ni, nj) (host logic, no device work) says whether an
+ * (ni, nj) slab is in it. */
+int npb_jacobi2d_block2_f64(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, double *dst2,
+                            int64_t tile_row_lo, int64_t tile_row_hi);
+int npb_jacobi2d_block_marches(int64_t ni, int64_t nj);
 /* mode & 7: 0 dispatch by size (grids that fit on chip -- NPBench S / M / L -- run in ONE cooperative launch:
  * jacobi2d_regtile_kernel, cell state in registers, T sweeps per halo exchange through in-L2 inboxes; grids of
  * >= 14M cells: marching passes, jacobi2d_march_kernel, 3/5/7 sweeps per pass in registers; else blocked
@@ -117,6 +125,7 @@ int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src
  * mode >> 8 = rows per chunk of the marching kernel (0 = auto) */
 int npb_jacobi2d_set_mode(int mode);
 int npb_jacobi2d_last_path(void);        /* 1 register-tile resident kernel, 2 blocked passes, 3 marching passes */
+int npb_jacobi2d_last_passes(void);      /* passes over memory of the last npb_jacobi2d_f64 call (0 for the register-tile kernel) */
 /* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, sweeps per
  * halo exchange, tiles along i, tiles along j, CTAs per SM} */
 int npb_jacobi2d_regtile_config(int *out7);

@@ -285,6 +285,7 @@ int try_regtile(int64_t nsweeps, int64_t ni, int64_t nj, double *A, double *B) {
 int g_jacobi_mode = 0;      // 0 dispatch by size (register-tile resident kernel when the grid fits on chip, marching passes
                             // for HBM-sized grids, blocked passes between), 1 blocked passes, 2 = 0, 3 marching passes
 int g_jacobi_last = 0;      // 1 register-tile resident kernel, 2 blocked passes, 3 marching passes
+int g_jacobi_passes = 0;    // passes over memory of the last npb_jacobi2d_f64 call
 int g_jacobi_rc = 0;        // rows per chunk override for the marching kernel
 
 template <class T>
@@ -352,6 +353,7 @@ constexpr long long JM_AUTO_MIN_CELLS = 14000000;  // default dispatch: measured
 // passes, 2 same as 0, 3 marching passes at any size; mode >> 8: rows per chunk of the marching kernel (0 = automatic)
 extern "C" int npb_jacobi2d_set_mode(int mode) { g_jacobi_mode = mode & 7; g_jacobi_rc = mode >> 8; return 0; }
 extern "C" int npb_jacobi2d_last_path(void) { return g_jacobi_last; }
+extern "C" int npb_jacobi2d_last_passes(void) { return g_jacobi_passes; }
 // configuration of the last register-tile launch: {rows per thread, columns per thread, warps per CTA, sweeps per
 // halo exchange, tiles along i, tiles along j, CTAs per SM}
 extern "C" int npb_jacobi2d_regtile_config(int *out7) {
@@ -373,6 +375,34 @@ extern "C" int npb_jacobi2d_regtile_plan(int64_t tsteps, int64_t ni, int64_t nj,
     return 1;
 }
 
+namespace {
+bool block_marches(int64_t ni, int64_t nj) {
+    return nj >= 8 && (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP));
+}
+}  // namespace
+
+// host logic only: 1 if npb_jacobi2d_block_f64 runs an (ni, nj) slab by marching passes (then npb_jacobi2d_block2_f64 exists for it)
+extern "C" int npb_jacobi2d_block_marches(int64_t ni, int64_t nj) { return (ni >= 3 && nj >= 3 && block_marches(ni, nj)) ? 1 : 0; }
+
+// npb_jacobi2d_block_f64 that ALSO stores the state before the last sweep of the pass into dst2 (interior cells of the
+// same rows): the closing pass of the slab driver leaves state S in A and state S - 1 in B without a separate single
+// sweep (see npb_jacobi2d_f64).  Marching regime only.
+extern "C" int npb_jacobi2d_block2_f64(int nsteps, int64_t ni, int64_t nj, const double *src, double *dst, double *dst2,
+                                       int64_t tile_row_lo, int64_t tile_row_hi) {
+    NPB_REQUIRE_INIT();
+    NPB_ARG(nsteps >= 3 && nsteps <= NPB_JACOBI2D_MAX_BLOCK && (nsteps & 1), "npb_jacobi2d_block2_f64",
+            "nsteps must be odd and in 3..7");
+    NPB_ARG(dst2 != nullptr && dst2 != dst && dst2 != src, "npb_jacobi2d_block2_f64", "dst2 must be a third array");
+    NPB_ARG(ni >= 3 && nj >= 3 && block_marches(ni, nj), "npb_jacobi2d_block2_f64",
+            "slab is not in the marching regime (ask npb_jacobi2d_block_marches first)");
+    const int64_t tiles_i = (ni - 2 + TileBig::TI - 1) / TileBig::TI;
+    if (tile_row_hi < 0 || tile_row_hi > tiles_i) tile_row_hi = tiles_i;
+    if (tile_row_lo < 0) tile_row_lo = 0;
+    const int64_t row_lo = 1 + tile_row_lo * TileBig::TI;
+    const int64_t row_hi = (tile_row_hi >= tiles_i) ? ni - 1 : 1 + tile_row_hi * TileBig::TI;
+    return launch_jm(nsteps, ni, nj, src, dst, g_jacobi_rc, row_lo, row_hi, dst2);
+}
+
 extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const double *src,
                                       double *dst, int64_t tile_row_lo, int64_t tile_row_hi) {
     NPB_REQUIRE_INIT();
@@ -382,8 +412,7 @@ extern "C" int npb_jacobi2d_block_f64(int nsteps, int64_t ni, int64_t nj, const 
     NPB_ARG(nj - 2 < (int64_t)TileBig::TJ * 2147483647LL, "npb_jacobi2d_block_f64", "row too long");
     if (ni < 3 || nj < 3) return 0;   // no interior
     // big slabs: the same rows by marching passes (tile rows -> interior rows [1 + lo*TI, 1 + hi*TI))
-    if (nj >= 8 &&
-        (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP))) {
+    if (block_marches(ni, nj)) {
         const int64_t tiles_i = (ni - 2 + TileBig::TI - 1) / TileBig::TI;
         if (tile_row_hi < 0 || tile_row_hi > tiles_i) tile_row_hi = tiles_i;
         if (tile_row_lo < 0) tile_row_lo = 0;
@@ -563,7 +592,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
         const int r = try_regtile(2 * (tsteps - 1), ni, nj, A, B);
         if (r < 0) return npb::fail("npb_jacobi2d_f64", "cooperative launch of jacobi2d_regtile_kernel failed (is the GPU "
                                                         "shared with other work?); no silent fallback to the slow path");
-        if (r == 1) { g_jacobi_last = 1; return 0; }
+        if (r == 1) { g_jacobi_last = 1; g_jacobi_passes = 0; return 0; }
     }
     const bool march = (g_jacobi_mode == 3 || (g_jacobi_mode == 0 && ni * nj >= JM_AUTO_MIN_CELLS && nj >= 4 * JM_STRIP)) &&
                        tsteps >= 3 && nj >= 8;
@@ -590,6 +619,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
             memset(&keyd, 0, sizeof(keyd));
             keyd.kind = 3; keyd.dims[0] = tsteps; keyd.dims[1] = ni; keyd.dims[2] = nj; keyd.dims[3] = -1 - g_jacobi_rc;
             keyd.ptrs[0] = A; keyd.ptrs[1] = B; keyd.ptrs[2] = W;
+            g_jacobi_passes = (int)k;
             const bool graphd = (k >= 8) && ni * nj <= (1LL << 24);
             if (graphd && npb::graph_replay(keyd)) return 0;
             const bool capd_on = graphd && npb::graph_begin();
@@ -619,6 +649,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
     }
     int64_t n = (M + max_block - 1) / max_block;
     if ((n & 1) == 0) ++n;
+    g_jacobi_passes = (int)n + 1;
     int64_t extra_pairs = (M - n) / 2;            // distribute in units of 2 sweeps
     const int64_t cap = (max_block - 1) / 2;
     const int tile = pick_tile(ni, nj);

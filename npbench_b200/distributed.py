@@ -73,6 +73,22 @@ def jacobi_plan(total_sweeps: int, max_block: int = JACOBI_MAX_BLOCK) -> List[in
     return plan + [1]
 
 
+def jacobi_plan_dual(total_sweeps: int, max_block: int = JACOBI_MAX_BLOCK) -> List[int]:
+    """Split S (even) sweeps into an EVEN number of odd-sized passes, smaller ones first; the last pass stores
+    the states S and S - 1 (csrc/jacobi2d.cu: the scratch-grid plan of npb_jacobi2d_f64 -- the same sizes)."""
+    assert total_sweeps >= 2 and total_sweeps % 2 == 0
+    k = (total_sweeps + max_block - 1) // max_block
+    if k % 2:
+        k += 1
+    k = max(k, 2)
+    pairs, cap, plan = (total_sweeps - k) // 2, (max_block - 1) // 2, []
+    for p in range(k):
+        take = min(cap, pairs // (k - p))
+        pairs -= take
+        plan.append(1 + 2 * take)
+    return plan
+
+
 # --------------------------------------------------------------------------- communication
 class HaloExchanger:
     """Exchange H boundary rows of row-major slabs with rank-1 / rank+1."""
@@ -128,9 +144,17 @@ class B200Engine:
             self.lib.set_stream(self.compute.cuda_stream)
             fn(*args)
 
-    def jacobi_block(self, nsteps, src, dst, t_lo, t_hi):
-        self._launch(self.lib.jacobi2d_block_f64, nsteps, src.shape[0], src.shape[1], src.data_ptr(),
-                     dst.data_ptr(), t_lo, t_hi)
+    def jacobi_block(self, nsteps, src, dst, t_lo, t_hi, dst2=None):
+        if dst2 is None:
+            self._launch(self.lib.jacobi2d_block_f64, nsteps, src.shape[0], src.shape[1], src.data_ptr(),
+                         dst.data_ptr(), t_lo, t_hi)
+        else:       # the pass also stores the state before its last sweep (marching regime only)
+            self._launch(self.lib.jacobi2d_block2_f64, nsteps, src.shape[0], src.shape[1], src.data_ptr(),
+                         dst.data_ptr(), dst2.data_ptr(), t_lo, t_hi)
+
+    def jacobi_dual_ok(self, nrows, ncols) -> bool:
+        """True if a pass over an (nrows, ncols) slab can store two states (jacobi_block(..., dst2=...))."""
+        return bool(self.lib.jacobi2d_block_marches(nrows, ncols))
 
     def heat_sweep(self, src, dst, i_lo, i_hi):
         n0, n1, n2 = src.shape
@@ -212,19 +236,42 @@ def jacobi_2d_sharded(engine, slab: Slab, TSTEPS: int, A: torch.Tensor, B: torch
     assert slab.H >= JACOBI_MAX_BLOCK or slab.size == 1
     ex = exchanger or HaloExchanger(slab, group)
     tb, te, ntr = _boundary_tile_ranges(slab, engine.tile_rows)
-    src, dst = A, B
-    for n in jacobi_plan(2 * (TSTEPS - 1)):
-        if slab.size == 1:
-            engine.jacobi_block(n, src, dst, 0, ntr)
+    total = 2 * (TSTEPS - 1)
+
+    def one_pass(n, src, dst, dst2, exchange):
+        if slab.size == 1 or not exchange:
+            engine.jacobi_block(n, src, dst, 0, ntr, dst2)
         else:
             if tb > 0:
-                engine.jacobi_block(n, src, dst, 0, tb)
+                engine.jacobi_block(n, src, dst, 0, tb, dst2)
             if te < ntr:
-                engine.jacobi_block(n, src, dst, te, ntr)
+                engine.jacobi_block(n, src, dst, te, ntr, dst2)
             reqs = engine.start_exchange(ex, [dst], engine.boundary_done())
             if te > tb:
-                engine.jacobi_block(n, src, dst, tb, te)     # overlaps the halo transfer
+                engine.jacobi_block(n, src, dst, tb, te, dst2)     # overlaps the halo transfer
             engine.finish_exchange(reqs)
+
+    # Every rank must take the same decision: the thinnest slab of the partition decides whether the passes can store
+    # two states (marching regime).  Then an even number of passes A -> B -> ... -> A -> W -> (A, B) covers all sweeps:
+    # W, a scratch slab that stands in for B (it carries B's border ring), feeds the closing pass, which stores state
+    # S into A and state S - 1 into B -- the separate single sweep B -> A and its exchange disappear.
+    thinnest = min(Slab(slab.n_global, slab.size, r, slab.H).nloc for r in range(slab.size))
+    if total >= 4 and getattr(engine, "jacobi_dual_ok", None) and engine.jacobi_dual_ok(thinnest, A.shape[1]):
+        plan = jacobi_plan_dual(total)
+        W = engine.empty(*A.shape)
+        for sl in ((slice(None), slice(0, 1)), (slice(None), slice(-1, None)), (slice(0, 1), slice(None)),
+                   (slice(-1, None), slice(None))):
+            engine.copy(W[sl], B[sl])
+        k = len(plan)
+        for p, n in enumerate(plan):
+            last = p == k - 1
+            src = W if last else (B if p % 2 else A)
+            dst = A if last else (W if p == k - 2 else (A if p % 2 else B))
+            one_pass(n, src, dst, B if last else None, exchange=not last)
+        return
+    src, dst = A, B
+    for n in jacobi_plan(total):
+        one_pass(n, src, dst, None, exchange=True)
         src, dst = dst, src
 
 

@@ -25,11 +25,23 @@ class CpuEngine:
     def empty(self, *shape):
         return torch.full(shape, float("nan"), dtype=torch.float64)
 
-    def jacobi_block(self, n, src, dst, t_lo, t_hi):
+    dual = False           # True: the slab driver may use passes that store two states (marching regime on the GPU)
+
+    def jacobi_dual_ok(self, nrows, ncols):
+        return self.dual
+
+    def jacobi_block(self, n, src, dst, t_lo, t_hi, dst2=None):
         a, b = src.numpy().copy(), dst.numpy().copy()
-        oracle.jacobi_2d_sweeps(n, a, b)
-        res = b if n % 2 else a
         r0, r1 = 1 + t_lo * self.tile_rows, min(src.shape[0] - 1, 1 + t_hi * self.tile_rows)
+        if dst2 is not None:              # state n - 1 (even number of sweeps: it ends in `a`) -> dst2, then the last sweep
+            assert n % 2 == 1 and n >= 3
+            oracle.jacobi_2d_sweeps(n - 1, a, b)
+            dst2.numpy()[r0:r1, 1:-1] = a[r0:r1, 1:-1]
+            oracle.jacobi_2d_sweeps(1, a, b)
+            res = b
+        else:
+            oracle.jacobi_2d_sweeps(n, a, b)
+            res = b if n % 2 else a
         dst.numpy()[r0:r1, 1:-1] = res[r0:r1, 1:-1]
 
     def heat_sweep(self, src, dst, i_lo, i_hi):
@@ -109,14 +121,17 @@ def _worker(rank, size, port, case):
         eng = CpuEngine()
         rng = np.random.default_rng(1234)          # same stream on every rank
         if case == "jacobi":
-            for ts, (ni, nj) in ((2, (40, 13)), (6, (61, 30)), (12, (47, 19))):
-                A, B = rng.random((ni, nj)), rng.random((ni, nj))
-                slab = D.Slab(ni, size, rank, D.JACOBI_MAX_BLOCK)
-                lA, lB = _local(slab, A), _local(slab, B)
-                D.jacobi_2d_sharded(eng, slab, ts, lA, lB)
-                oracle.jacobi_2d(ts, A, B)
-                assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank)
-                assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank)
+            for ts, (ni, nj) in ((2, (40, 13)), (6, (61, 30)), (12, (47, 19)), (3, (44, 9))):
+                A0, B0 = rng.random((ni, nj)), rng.random((ni, nj))
+                for dual in (False, True):      # True: the closing pass stores the last two states (scratch slab W)
+                    A, B = A0.copy(), B0.copy()
+                    eng.dual = dual
+                    slab = D.Slab(ni, size, rank, D.JACOBI_MAX_BLOCK)
+                    lA, lB = _local(slab, A), _local(slab, B)
+                    D.jacobi_2d_sharded(eng, slab, ts, lA, lB)
+                    oracle.jacobi_2d(ts, A, B)
+                    assert np.array_equal(slab.owned(lA).numpy(), A[slab.lo:slab.hi]), ("A", ts, rank, dual)
+                    assert np.array_equal(slab.owned(lB).numpy(), B[slab.lo:slab.hi]), ("B", ts, rank, dual)
         elif case == "heat":
             for ts, shape, H in ((2, (14, 6, 7), 3), (5, (17, 5, 6), 4), (8, (25, 6, 5), 3), (7, (40, 5, 6), 3), (4, (36, 4, 5), 5)):
                 A, B = rng.random(shape), rng.random(shape)
@@ -171,6 +186,12 @@ def test_single_rank_driver_equals_kernel():
     D.jacobi_2d_sharded(eng, slab, 9, lA, lB)
     oracle.jacobi_2d(9, A, B)
     assert np.array_equal(lA.numpy(), A) and np.array_equal(lB.numpy(), B)
+    eng.dual = True                    # the scratch-slab plan on one rank
+    A2, B2 = rng.random((21, 17)), rng.random((21, 17))
+    lA, lB = torch.from_numpy(A2.copy()), torch.from_numpy(B2.copy())
+    D.jacobi_2d_sharded(eng, slab, 9, lA, lB)
+    oracle.jacobi_2d(9, A2, B2)
+    assert np.array_equal(lA.numpy(), A2) and np.array_equal(lB.numpy(), B2)
 
 
 def test_plan_matches_the_c_driver_rules():
@@ -179,6 +200,16 @@ def test_plan_matches_the_c_driver_rules():
         assert sum(plan) == 2 * (ts - 1)
         assert all(p % 2 == 1 and 1 <= p <= 7 for p in plan)
         assert len(plan) % 2 == 0 and (not plan or plan[-1] == 1)
+
+
+def test_dual_plan_rules():
+    """an even number of odd passes of at most 7 sweeps, ascending, that cover all sweeps (csrc/jacobi2d.cu: the
+    scratch-grid plan of npb_jacobi2d_f64)"""
+    for ts in range(2, 60):
+        plan = D.jacobi_plan_dual(2 * (ts - 1))
+        assert sum(plan) == 2 * (ts - 1) and len(plan) % 2 == 0
+        assert all(p % 2 == 1 and 1 <= p <= 7 for p in plan) and plan == sorted(plan)
+    assert D.jacobi_plan_dual(40) == [5, 7, 7, 7, 7, 7]
 
 
 def test_slab_bounds_cover_without_overlap():

@@ -96,8 +96,12 @@ def _dev(full, slab):
     return torch.from_numpy(np.ascontiguousarray(full[slab.row0:slab.row0 + slab.nloc])).cuda()
 
 
+@pytest.mark.parametrize("march", [False, True], ids=["blocked", "marching-dual"])
 @pytest.mark.parametrize("size", [2, 3])
-def test_jacobi_sharded_on_gpu(D, size):
+def test_jacobi_sharded_on_gpu(D, size, march):
+    """march: marching passes forced on the small slabs; the driver then runs the scratch-slab plan whose closing
+    pass stores the last two states (npb_jacobi2d_block2_f64)."""
+    import npbench_b200 as nb
     rng = np.random.default_rng(1)
     ni, nj, ts = 333, 270, 12
     A, B = rng.random((ni, nj)), rng.random((ni, nj))
@@ -108,12 +112,18 @@ def test_jacobi_sharded_on_gpu(D, size):
     def body(r):
         eng = D.B200Engine(0)
         slab = D.Slab(ni, size, r, D.JACOBI_MAX_BLOCK)
+        assert eng.jacobi_dual_ok(slab.nloc, nj) == march
         lA, lB = _dev(A, slab), _dev(B, slab)
         D.jacobi_2d_sharded(eng, slab, ts, lA, lB, exchanger=LoopbackExchanger(slab, mb))
         eng.synchronize()
         out[r] = (slab, slab.owned(lA).cpu().numpy(), slab.owned(lB).cpu().numpy())
 
-    run_ranks(size, body)
+    nb.init(0)
+    nb.lib().jacobi2d_set_mode(3 if march else 0)
+    try:
+        run_ranks(size, body)
+    finally:
+        nb.lib().jacobi2d_set_mode(0)
     for r, (slab, a, b) in out.items():
         assert_bit_equal(a, wA[slab.lo:slab.hi], "A rank %d" % r)
         assert_bit_equal(b, wB[slab.lo:slab.hi], "B rank %d" % r)
