@@ -886,7 +886,7 @@ def multi_gpu(args, world, rank, local_rank):
     suite = multi_gpu_suite(args, world, rank, eng, D, torch, dist, peak) if not args.no_suite else None
 
     # dominant kernel: the multi-sweep jacobi pass (up to 7 sweeps fused): 16 B x cells x sweeps per launch
-    n_pass = max(1, len(D.jacobi_plan(WEAK_SWEEPS)))
+    n_pass = max(1, len(D.jacobi_plan_dual(WEAK_SWEEPS) if eng.jacobi_dual_ok(slab.nloc, WEAK_COLS) else D.jacobi_plan(WEAK_SWEEPS)))
     achieved = value * 16.0 / world
     tr = traffic.get("jacobi_2d_weak_bytes_per_launch")
     pass_us = ms * 1e3 / n_pass
