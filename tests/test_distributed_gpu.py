@@ -45,6 +45,10 @@ class _Recv:
         data, ev = self.mb.take(self.key)
         ev.wait()                      # current (compute) stream waits for the sender's copy
         self.dst.copy_(data)
+        # `data` was allocated on the sender's comm stream: tell the caching allocator that this stream reads it, or the
+        # block may be handed out again before the copy above has run (seen under compute-sanitizer, where the GPU
+        # lags far behind the host threads)
+        data.record_stream(torch.cuda.current_stream())
 
 
 class LoopbackExchanger:
