@@ -356,6 +356,7 @@ int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, in
     if (env_rc > 0) rc = env_rc;
     if (rc_override > 0) rc = rc_override;
     if (rc > rows) rc = rows;
+    if ((rows + rc - 1) / rc > 65535) rc = (rows + 65534) / 65535;      // gridDim.y limit: longer chunks on very tall grids
     const long long chunks = (rows + rc - 1) / rc;
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("jacobi2d", "grid too large");
     static const int pfd = getenv("NPB_J2_PFD") ? atoi(getenv("NPB_J2_PFD")) : 3;
