@@ -2,7 +2,9 @@
 
     python tools/heat_trace.py [N [TSTEPS]]
 Prints, for thread 0 (a corner block: two halo sides) and the middle thread, the average cycles per sweep spent in
-[faces + halo-independent arithmetic | waiting for halo values | halo-dependent arithmetic + sends | re-arm + publish | fence + barrier].
+[faces + halo-independent arithmetic | waiting for halo values | halo-dependent arithmetic + sends | re-arm + publish | fence + barrier],
+the %globaltimer timeline of the centre CTA (load | sweep 1 | sweeps 2 - 17 | the rest | store), the spread of the entry and
+exit times of all CTAs, and the CUDA-event time of the same call (L2 flushed in front of it, like bench.py does).
 """
 import ctypes
 import os
