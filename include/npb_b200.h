@@ -126,6 +126,11 @@ int npb_jacobi2d_block_marches(int64_t ni, int64_t nj);
 int npb_jacobi2d_set_mode(int mode);
 int npb_jacobi2d_last_path(void);        /* 1 register-tile resident kernel, 2 blocked passes, 3 marching passes */
 int npb_jacobi2d_last_passes(void);      /* passes over memory of the last npb_jacobi2d_f64 call (0 for the register-tile kernel) */
+/* host logic only (no device work): the passes npb_jacobi2d_f64 runs a grid in the marching regime with.  dual != 0: the
+ * scratch-grid plan (an even number of odd passes, the last one stores the states S and S - 1); dual == 0: the plan
+ * used without scratch memory (odd passes + a closing single sweep).  Writes min(passes, cap) entries, returns the
+ * number of passes. */
+int npb_jacobi2d_pass_plan(int64_t tsteps, int dual, int32_t *sweeps, int cap);
 /* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, sweeps per
  * halo exchange, tiles along i, tiles along j, CTAs per SM} */
 int npb_jacobi2d_regtile_config(int *out7);

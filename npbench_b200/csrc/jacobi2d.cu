@@ -464,7 +464,41 @@ int jacobi_pass_plan(int64_t tsteps, int64_t max_block, int *ns, int cap) {
     return (int)(n + 1);
 }
 
+// the scratch-grid plan of npb_jacobi2d_f64 (marching): an EVEN number of odd passes, the smaller ones first, covering
+// all S = 2 (TSTEPS - 1) sweeps; the last one stores two states (npbench_b200/distributed.py: jacobi_plan_dual)
+int jacobi_pass_plan_dual(int64_t S, int64_t max_block, int *ns, int cap) {
+    if (S < 2 || (S & 1)) return -1;
+    int64_t k = (S + max_block - 1) / max_block;
+    if (k & 1) ++k;
+    if (k < 2) k = 2;
+    if (k > cap) return -1;
+    int64_t pairs = (S - k) / 2;
+    const int64_t lim = (max_block - 1) / 2;
+    for (int64_t p = 0; p < k; ++p) {
+        int64_t take = pairs / (k - p);               // the smaller passes first: the closing DUAL pass gets the most
+        if (take > lim) take = lim;                   // sweeps (its 7-sweep instantiation has no spills, the 5-sweep one has)
+        pairs -= take;
+        ns[p] = (int)(1 + 2 * take);
+    }
+    return (int)k;
+}
+
 }  // namespace
+
+// host logic only (no device work): the passes npb_jacobi2d_f64 runs a grid in the marching regime with -- dual != 0: the
+// scratch-grid plan (the last pass stores two states), else the round-1 plan (odd passes + a closing single sweep).
+// Writes min(passes, cap) entries, returns the number of passes (0: no sweeps).
+extern "C" int npb_jacobi2d_pass_plan(int64_t tsteps, int dual, int32_t *sweeps, int cap) {
+    if (tsteps < 2 || !sweeps || cap < 0) return 0;
+    static const int march_max = getenv("NPB_J2_MAXNS") ? atoi(getenv("NPB_J2_MAXNS")) : 7;
+    const int64_t max_block = march_max >= 7 ? 7 : march_max >= 5 ? 5 : 3;
+    std::vector<int> ns((size_t)(2 * tsteps + 4));
+    const int n = (dual && 2 * (tsteps - 1) >= 4) ? jacobi_pass_plan_dual(2 * (tsteps - 1), max_block, ns.data(), (int)ns.size())
+                                                  : jacobi_pass_plan(tsteps, max_block, ns.data(), (int)ns.size());
+    if (n < 0) return 0;
+    for (int q = 0; q < n && q < cap; ++q) sweeps[q] = ns[q];
+    return n;
+}
 
 int npb::jacobi2d_host_pipelined(int64_t tsteps, int64_t ni, int64_t nj, double *A, double *B) {
     // experiments / tests (read at every call): smallest grid that is pipelined, rows per chunk
@@ -610,11 +644,9 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
         double *W = (double *)npb::workspace(9, (size_t)ni * (size_t)nj * sizeof(double));
         if (W) {
             const int64_t S = M + 1;
-            int64_t k = (S + max_block - 1) / max_block;
-            if (k & 1) ++k;
-            if (k < 2) k = 2;
-            int64_t pairs = (S - k) / 2;
-            const int64_t capd = (max_block - 1) / 2;
+            std::vector<int> plan((size_t)S + 2);
+            const int64_t k = jacobi_pass_plan_dual(S, max_block, plan.data(), (int)plan.size());
+            if (k < 2) return npb::fail("npb_jacobi2d_f64", "pass plan failed");
             npb::GraphKey keyd;
             memset(&keyd, 0, sizeof(keyd));
             keyd.kind = 3; keyd.dims[0] = tsteps; keyd.dims[1] = ni; keyd.dims[2] = nj; keyd.dims[3] = -1 - g_jacobi_rc;
@@ -631,11 +663,7 @@ extern "C" int npb_jacobi2d_f64(int64_t tsteps, int64_t ni, int64_t nj, double *
                 else npb::count_launch();
             }
             for (int64_t p = 0; p < k && !rc; ++p) {
-                const int64_t left = k - p;
-                int64_t take = pairs / left;                  // the smaller passes first: the closing DUAL pass gets the most
-                if (take > capd) take = capd;                 // sweeps (its 7-sweep instantiation has no spills, the 5-sweep one has)
-                pairs -= take;
-                const int ns = (int)(1 + 2 * take);
+                const int ns = plan[(size_t)p];
                 const double *src = (p == k - 1) ? W : ((p & 1) ? B : A);
                 double *dst = (p == k - 1) ? A : (p == k - 2) ? W : ((p & 1) ? A : B);
                 rc = launch_jm(ns, ni, nj, src, dst, g_jacobi_rc, 0, -1, (p == k - 1) ? B : nullptr);

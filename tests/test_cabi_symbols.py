@@ -92,3 +92,33 @@ def test_fdtd2d_pass_plan_host_logic():
     # cap smaller than the plan: count is still returned, only `cap` entries are written
     buf[:] = -1
     assert L.fdtd2d_pass_plan(50, 1, ptr, 3) == 10 and buf[:4].tolist() == [5, 5, 5, -1]
+
+
+def test_jacobi2d_pass_plan_host_logic_matches_the_slab_driver():
+    """npb_jacobi2d_pass_plan is pure host logic: the passes of the single-device call in the marching regime are the
+    slab driver's (distributed.jacobi_plan / jacobi_plan_dual) -- same sizes, same order -- so that N = 1 and N > 1 run
+    the same plan, and they cover 2 (TSTEPS - 1) sweeps with odd passes of at most 7 sweeps."""
+    import ctypes
+
+    import numpy as np
+
+    from npbench_b200 import _lib
+    from npbench_b200 import distributed as D
+
+    L = _lib.lib()
+    buf = np.zeros(4096, dtype=np.int32)
+    ptr = ctypes.c_void_p(buf.ctypes.data)
+    assert L.jacobi2d_pass_plan(1, 1, ptr, buf.size) == 0
+    for ts in list(range(2, 80)) + [500, 1000]:
+        S = 2 * (ts - 1)
+        n = L.jacobi2d_pass_plan(ts, 0, ptr, buf.size)
+        assert buf[:n].tolist() == D.jacobi_plan(S), ts
+        n = L.jacobi2d_pass_plan(ts, 1, ptr, buf.size)
+        plan = buf[:n].tolist()
+        assert sum(plan) == S and all(p % 2 == 1 and 1 <= p <= 7 for p in plan), ts
+        if S >= 4:
+            assert plan == D.jacobi_plan_dual(S) and n % 2 == 0 and plan[-1] >= 3, ts
+        else:
+            assert plan == D.jacobi_plan(S), ts           # two sweeps: nothing to gain from a scratch grid
+    buf[:] = -1
+    assert L.jacobi2d_pass_plan(21, 1, ptr, 2) == 6 and buf[:3].tolist() == [5, 7, -1]
