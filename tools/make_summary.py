@@ -58,6 +58,12 @@ def main():
         rows = "; ".join("%s %.0f%s" % (r["kernel"], r["value"], (" (%.2f)" % r["weak_scaling_efficiency"]) if "weak_scaling_efficiency" in r else "")
                          for r in (m.get("suite") or []))
         out.append("| %d | %.0f | %.0f | %.3f | %s | %s | %s |" % (n, m["value"], one, m["value"] / (n * one), m["e2e"].get("value"), m["parity"]["bit_exact"], rows))
+    for n in (2, 4, 8):         # re-runs late in the round (headline only), after the last kernel changes
+        m = line("r%s_bench_n%d_late.json" % (rr, n))
+        if m:
+            one = m["single_gpu_same_workload"]["value"]
+            out.append("| %d (late re-run: short chunks + two-state closing pass) | %.0f | %.0f | %.3f | %s | %s | — |" % (
+                n, m["value"], one, m["value"] / (n * one), m["e2e"].get("value"), m["parity"]["bit_exact"]))
     for n in (2, 4, 8):
         p = os.path.join(P, "r%s_check_multigpu_n%d.log" % (rr, n))
         if os.path.exists(p):
