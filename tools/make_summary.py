@@ -72,6 +72,25 @@ def main():
     p = os.path.join(P, "r%s_pytest_gpu.log" % rr)
     if os.path.exists(p):
         out += ["", "## tests", "", "`pytest -m gpu`: %s" % open(p).read().strip().splitlines()[-1]]
+    p = os.path.join(P, "r%s_launches_bench.csv" % rr)
+    if os.path.exists(p):
+        import collections
+        import csv
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        scale = {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0}
+        for r in csv.reader(open(p)):
+            if len(r) > 10 and r[0].isdigit():
+                a = agg[r[4].split("(")[0].replace("<unnamed>::", "")]
+                a[0] += 1
+                a[1] += float(r[-1].replace(",", "")) * scale.get(r[-2], 1e-6)
+        tot = sum(v[1] for v in agg.values()) or 1.0
+        out += ["", "## ncu launch list of the bench command (`r%s_launches_bench.csv`: first 600 launches of `bench.py --steps 2 --warmup 1`, "
+                "`gpu__time_duration.sum`, cold caches, serialised)" % rr, "",
+                "The timed headline steps are the full-grid `jacobi2d_march_kernel<7, 1, 0>` / `<5, 1, 0>` / `<7, 1, 1>` (two-state closing pass) launches; "
+                "the many short `<5, 1, 0>` / `<1, 1, 0>` launches are the row-chunk pipeline of the e2e host-buffer call.", "",
+                "| kernel | launches | total ms | share |", "|---|---|---|---|"]
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]:
+            out.append("| `%s` | %d | %.3f | %.1f %% |" % (k, v[0], v[1], 100.0 * v[1] / tot))
     out += ["", "## ncu summaries in this directory", ""]
     for f in sorted(os.listdir(P)):
         if f.startswith("r%s_ncu_" % rr) and f.endswith(".txt"):
