@@ -131,6 +131,9 @@ int npb_jacobi2d_last_passes(void);      /* passes over memory of the last npb_j
  * used without scratch memory (odd passes + a closing single sweep).  Writes min(passes, cap) entries, returns the
  * number of passes. */
 int npb_jacobi2d_pass_plan(int64_t tsteps, int dual, int32_t *sweeps, int cap);
+/* host logic only: rows per chunk (gridDim.y = ceil(rows / this)) of one marching launch of `ns` (1, 3, 5, 7) sweeps over
+ * `rows` rows of an nj-column grid on `sms` SMs; 0 for arguments out of range */
+int64_t npb_jacobi2d_march_rows_per_chunk(int ns, int64_t rows, int64_t nj, int sms);
 /* configuration of the last register-tile launch: {rows, columns of cells per thread, warps per CTA, sweeps per
  * halo exchange, tiles along i, tiles along j, CTAs per SM} */
 int npb_jacobi2d_regtile_config(int *out7);

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "npb_jacobi2d_last_path": (_int, []),
     "npb_jacobi2d_last_passes": (_int, []),
     "npb_jacobi2d_pass_plan": (_int, [_i64, _int, _vp, _int]),
+    "npb_jacobi2d_march_rows_per_chunk": (_i64, [_int, _i64, _i64, _int]),
     "npb_jacobi2d_regtile_config": (_int, [_vp]),
     "npb_jacobi2d_regtile_plan": (_int, [_i64, _i64, _i64, _int, _vp]),
     "npb_jacobi2d_tile_rows": (_int, []),
@@ -104,7 +105,7 @@ PROTOTYPES = {
 }
 
 _NO_STATUS = {"npb_version", "npb_last_error", "npb_get_stream", "npb_launch_count", "npb_mg_count", "npb_mg_current",
-              "npb_jacobi2d_tile_rows", "npb_jacobi2d_regtile_plan", "npb_fdtd2d_regtile_plan", "npb_jacobi2d_last_path", "npb_jacobi2d_last_passes", "npb_jacobi2d_pass_plan", "npb_jacobi2d_block_marches", "npb_seidel2d_last_path", "npb_heat3d_last_path", "npb_fdtd2d_last_path", "npb_fdtd2d_pass_plan", "npb_hdiff_last_path", "npb_vadv_last_path"}
+              "npb_jacobi2d_tile_rows", "npb_jacobi2d_regtile_plan", "npb_fdtd2d_regtile_plan", "npb_jacobi2d_last_path", "npb_jacobi2d_last_passes", "npb_jacobi2d_pass_plan", "npb_jacobi2d_march_rows_per_chunk", "npb_jacobi2d_block_marches", "npb_seidel2d_last_path", "npb_heat3d_last_path", "npb_fdtd2d_last_path", "npb_fdtd2d_pass_plan", "npb_hdiff_last_path", "npb_vadv_last_path"}
 
 
 class B200Error(RuntimeError):

@@ -381,6 +381,12 @@ bool block_marches(int64_t ni, int64_t nj) {
 }
 }  // namespace
 
+// host logic only: rows per chunk of one marching launch of `ns` sweeps over `rows` rows x nj columns on `sms` SMs
+extern "C" int64_t npb_jacobi2d_march_rows_per_chunk(int ns, int64_t rows, int64_t nj, int sms) {
+    if (!(ns == 1 || ns == 3 || ns == 5 || ns == 7) || rows < 1 || nj < 1 || sms < 1) return 0;
+    return (int64_t)jm_rows_per_chunk(ns, rows, nj, sms, g_jacobi_rc);
+}
+
 // host logic only: 1 if npb_jacobi2d_block_f64 runs an (ni, nj) slab by marching passes (then npb_jacobi2d_block2_f64 exists for it)
 extern "C" int npb_jacobi2d_block_marches(int64_t ni, int64_t nj) { return (ni >= 3 && nj >= 3 && block_marches(ni, nj)) ? 1 : 0; }
 

@@ -329,6 +329,32 @@ int launch_jm_ns(const JmParams &p, dim3 grid, bool vec) {
     return 0;
 }
 
+// Rows per chunk of one marching launch over `rows` rows of an nj-column grid on `sms` SMs (pure host logic; exported as
+// npb_jacobi2d_march_rows_per_chunk for the CPU tests).
+inline long long jm_rows_per_chunk(int ns, long long rows, long long nj, int sms, int rc_override) {
+    const long long out_cols = jm_out_cols(ns);
+    const long long nstrips = (nj + out_cols - 1) / out_cols;
+    const long long blocks_x = (nstrips + JM_WARPS - 1) / JM_WARPS;
+    // Rows per chunk.  Short chunks win by a wide margin although every chunk re-runs 2 * ns ramp rows: the warps of
+    // neighbouring strips start a chunk on the same rows and drift apart as they march, and with them the DRAM pages
+    // and the shared halo columns they touch.  Measured (ns = 5 / 7, B200): the 10240 x 81920 slab 33.1 ms per 40 sweeps
+    // at 1024 rows per chunk (the round-1 rule: ~48 warps per SM over the launch), 26.2 at 256, 25.6 at 192, 25.9 at
+    // 128, 27.2 at 64; 16384^2: 11.1 ms at 335 rows, 9.6 at 128, 9.5 at 96, 9.6 at 64, 10.6 at 32.  Hence ~256 warps
+    // per SM over the launch, at least 96 (small grids: 64) rows.  NPB_J2_CHUNKS / NPB_J2_RC override the rule / the rows per chunk.
+    static const int rule = getenv("NPB_J2_CHUNKS") ? atoi(getenv("NPB_J2_CHUNKS")) : 256;
+    static const int env_rc = getenv("NPB_J2_RC") ? atoi(getenv("NPB_J2_RC")) : 0;
+    const long long chunks0 = ((long long)rule * sms + nstrips - 1) / nstrips;
+    long long rc = (rows + chunks0 - 1) / chunks0;
+    // (64 rows where 96 would leave fewer than ~12 CTAs per SM over the launch: 4096^2 2.67 ms at 64, 3.08 ms at 96)
+    const long long rc_min = (blocks_x * (rows / 96) >= 12LL * sms) ? 96 : 64;
+    if (rc < rc_min) rc = rc_min;
+    if (env_rc > 0) rc = env_rc;
+    if (rc_override > 0) rc = rc_override;
+    if (rc > rows) rc = rows;
+    if ((rows + rc - 1) / rc > 65535) rc = (rows + 65534) / 65535;      // gridDim.y limit: longer chunks on very tall grids
+    return rc;
+}
+
 // one pass: ns (1, 3, 5 or 7) sweeps src -> dst; dst2 != nullptr: the state before the last sweep goes there as well
 int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, int rc_override, int64_t row_lo = 0,
               int64_t row_hi = -1, double *dst2 = nullptr) {
@@ -340,23 +366,7 @@ int launch_jm(int ns, int64_t ni, int64_t nj, const double *src, double *dst, in
     const long long nstrips = (nj + out_cols - 1) / out_cols;
     const long long blocks_x = (nstrips + JM_WARPS - 1) / JM_WARPS;
     const bool vec = (nj % 2 == 0) && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)dst2) % 16 == 0);
-    // Rows per chunk.  Short chunks win by a wide margin although every chunk re-runs 2 * ns ramp rows: the warps of
-    // neighbouring strips start a chunk on the same rows and drift apart as they march, and with them the DRAM pages
-    // and the shared halo columns they touch.  Measured (ns = 5 / 7, B200): the 10240 x 81920 slab 33.1 ms per 40 sweeps
-    // at 1024 rows per chunk (the round-1 rule: ~48 warps per SM over the launch), 26.2 at 256, 25.6 at 192, 25.9 at
-    // 128, 27.2 at 64; 16384^2: 11.1 ms at 335 rows, 9.6 at 128, 9.5 at 96, 9.6 at 64, 10.6 at 32.  Hence ~256 warps
-    // per SM over the launch, at least 96 (small grids: 64) rows.  NPB_J2_CHUNKS / NPB_J2_RC override the rule / the rows per chunk.
-    static const int rule = getenv("NPB_J2_CHUNKS") ? atoi(getenv("NPB_J2_CHUNKS")) : 256;
-    static const int env_rc = getenv("NPB_J2_RC") ? atoi(getenv("NPB_J2_RC")) : 0;
-    const long long chunks0 = ((long long)rule * npb::st().sm_count + nstrips - 1) / nstrips;
-    long long rc = (rows + chunks0 - 1) / chunks0;
-    // (64 rows where 96 would leave fewer than ~12 CTAs per SM over the launch: 4096^2 2.67 ms at 64, 3.08 ms at 96)
-    const long long rc_min = (blocks_x * (rows / 96) >= 12LL * npb::st().sm_count) ? 96 : 64;
-    if (rc < rc_min) rc = rc_min;
-    if (env_rc > 0) rc = env_rc;
-    if (rc_override > 0) rc = rc_override;
-    if (rc > rows) rc = rows;
-    if ((rows + rc - 1) / rc > 65535) rc = (rows + 65534) / 65535;      // gridDim.y limit: longer chunks on very tall grids
+    const long long rc = jm_rows_per_chunk(ns, rows, nj, npb::st().sm_count, rc_override);
     const long long chunks = (rows + rc - 1) / rc;
     if (blocks_x >= (1LL << 31) || chunks > 65535) return npb::fail("jacobi2d", "grid too large");
     static const int pfd = getenv("NPB_J2_PFD") ? atoi(getenv("NPB_J2_PFD")) : 3;

@@ -122,3 +122,25 @@ def test_jacobi2d_pass_plan_host_logic_matches_the_slab_driver():
             assert plan == D.jacobi_plan(S), ts           # two sweeps: nothing to gain from a scratch grid
     buf[:] = -1
     assert L.jacobi2d_pass_plan(21, 1, ptr, 2) == 6 and buf[:3].tolist() == [5, 7, -1]
+
+
+def test_jacobi2d_march_chunk_rule_host_logic():
+    """npb_jacobi2d_march_rows_per_chunk (pure host logic): short chunks (~256 warps per SM over a launch, at least 96
+    rows, 64 on small grids), never more rows than the launch has, never more than 65535 chunks."""
+    from npbench_b200 import _lib
+
+    L = _lib.lib()
+    f = L.jacobi2d_march_rows_per_chunk
+    assert f(2, 100, 100, 148) == 0 and f(7, 0, 100, 148) == 0
+    assert f(7, 10238, 81920, 148) == 197          # the bench slab: 52 chunks of 197 rows
+    assert f(7, 16382, 16384, 148) == 96           # 16384^2: the 96-row floor
+    assert f(7, 4094, 4096, 148) == 64             # 4096^2: too few strips for 96-row chunks
+    assert f(5, 40, 100000, 148) == 40             # a boundary range of the slab driver: one chunk
+    for ns in (1, 3, 5, 7):
+        for rows in (1, 63, 64, 200, 5000, 10 ** 6, 7 * 10 ** 6, 5 * 10 ** 7):
+            for nj in (8, 130, 4096, 81920, 10 ** 6):
+                for sms in (1, 132, 148):
+                    rc = f(ns, rows, nj, sms)
+                    assert 1 <= rc <= rows
+                    assert (rows + rc - 1) // rc <= 65535
+                    assert rc >= min(rows, 64)
